@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE — ctypes access to the CPU oracle (liboracle.so, prefix orc_) and, when it was built
+from /root/reference, the unmodified reference cpu_engine path (oracle/_ref/libhala_ref*.so, prefix ref_/refc_).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CODE = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}
+REAL = {0: np.float32, 1: np.float64, 2: np.float32, 3: np.float64}
+OPS = {"copy": 0, "axpy": 1, "scal": 2, "dot": 3, "dotu": 4, "nrm2": 5}
+
+
+def build(with_ref=True):
+    """Compile liboracle.so and (only where /root/reference exists) oracle/_ref/*.so. Building the checker is not using it."""
+    subprocess.run(["make", "-C", HERE, "liboracle.so"] + (["ref"] if with_ref else []), check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _scalar(v, dt):
+    return np.array([v], dtype=dt)
+
+
+class _Lib:
+    def __init__(self, path, prefix, has_cproj):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.has_cproj = has_cproj
+        self.version = C.cast(getattr(self.lib, prefix + "version"), C.CFUNCTYPE(C.c_char_p))().decode()
+
+    def _f(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+    def spmv(self, pntr, indx, vals, x, alpha=1.0, beta=0.0, y=None, trans="N", ncols=None):
+        dt = vals.dtype
+        M = pntr.size - 1
+        N = ncols if ncols is not None else M
+        out = np.zeros(M if trans == "N" else N, dtype=dt) if y is None else np.array(y, dtype=dt, copy=True)
+        a, b = _scalar(alpha, dt), _scalar(beta, dt)
+        rc = self._f("spmv")(CODE[dt], C.c_char(trans.encode()), M, N, _ptr(a), int(indx.size), _ptr(pntr), _ptr(indx),
+                             _ptr(vals), _ptr(np.ascontiguousarray(x, dtype=dt)), _ptr(b), _ptr(out))
+        assert rc == 0, rc
+        return out
+
+    def cg(self, pntr, indx, vals, b, tol, max_iter=10**6, x0=None):
+        dt = vals.dtype
+        n = pntr.size - 1
+        x = np.zeros(n, dtype=dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
+        it = C.c_int(0)
+        rc = self._f("cg")(CODE[dt], n, int(indx.size), _ptr(pntr), _ptr(indx), _ptr(vals),
+                           _ptr(np.ascontiguousarray(b, dtype=dt)), _ptr(x), C.c_double(tol), int(max_iter), C.byref(it))
+        assert rc == 0, rc
+        return x, it.value
+
+    def gmres(self, pntr, indx, vals, b, tol, restart, max_outer=10**6, x0=None, cproj=0):
+        dt = vals.dtype
+        n = pntr.size - 1
+        x = np.zeros(n, dtype=dt) if x0 is None else np.array(x0, dtype=dt, copy=True)
+        it = C.c_int(0)
+        args = [CODE[dt], n, int(indx.size), _ptr(pntr), _ptr(indx), _ptr(vals),
+                _ptr(np.ascontiguousarray(b, dtype=dt)), _ptr(x), C.c_double(tol), int(max_outer), int(restart)]
+        if self.has_cproj:
+            args.append(int(cproj))
+        rc = self._f("gmres")(*args, C.byref(it))
+        assert rc == 0, rc
+        return x, it.value
+
+    def blas1(self, op, x, y=None, alpha=1.0, n=None, incx=1, incy=1):
+        dt = x.dtype
+        code = CODE[dt]
+        n = (1 + (x.size - 1) // incx if x.size else 0) if n is None else n
+        a = _scalar(alpha, dt)
+        yy = None if y is None else np.array(y, dtype=dt, copy=True)
+        res = np.zeros(1, dtype=REAL[code] if op == "nrm2" else dt)
+        # scal works in place on the y slot
+        xx = np.ascontiguousarray(x)
+        if op == "scal":
+            yy = np.array(x, dtype=dt, copy=True)
+            incy = incx
+        rc = self._f("blas1")(code, OPS[op], int(n), _ptr(a), _ptr(xx), int(incx),
+                              _ptr(yy) if yy is not None else None, int(incy), _ptr(res))
+        assert rc == 0, rc
+        return res[0] if op in ("dot", "dotu", "nrm2") else yy
+
+    def gemv(self, trans, M, N, A, x, alpha=1.0, beta=0.0, y=None, lda=None):
+        dt = A.dtype
+        lda = M if lda is None else lda
+        out = np.zeros(M if trans == "N" else N, dtype=dt) if y is None else np.array(y, dtype=dt, copy=True)
+        a, b = _scalar(alpha, dt), _scalar(beta, dt)
+        rc = self._f("gemv")(CODE[dt], C.c_char(trans.encode()), M, N, _ptr(a), _ptr(np.ascontiguousarray(A)), int(lda),
+                             _ptr(np.ascontiguousarray(x, dtype=dt)), _ptr(b), _ptr(out))
+        assert rc == 0, rc
+        return out
+
+
+_cache = {}
+
+
+def _preload_blas_deps():
+    """The wheel's OpenBLAS needs the libgfortran/libquadmath that sit beside it but carries no RUNPATH for them."""
+    import glob
+    import sysconfig
+    d = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
+    for pat in ("libquadmath-*.so*", "libgfortran-*.so*"):
+        for f in sorted(glob.glob(os.path.join(d, pat))):
+            try:
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+
+
+def oracle():
+    """The plain-C restatement (always available once built)."""
+    if "orc" not in _cache:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(with_ref=False)
+        _cache["orc"] = _Lib(path, "orc_", True)
+    return _cache["orc"]
+
+
+def reference(cpatch=False):
+    """The unmodified reference cpu_engine path, or None when oracle/_ref was never built (no /root/reference)."""
+    key = "refc" if cpatch else "ref"
+    if key not in _cache:
+        path = os.path.join(HERE, "_ref", "libhala_ref_cpatch.so" if cpatch else "libhala_ref.so")
+        try:
+            _preload_blas_deps()
+            _cache[key] = _Lib(path, "refc_" if cpatch else "ref_", False) if os.path.exists(path) else None
+        except OSError:
+            _cache[key] = None
+    return _cache[key]
