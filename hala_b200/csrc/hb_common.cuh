@@ -1,0 +1,231 @@
+// hb_common.cuh — shared device/host helpers of libhalab200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/halab200.h"
+
+// ----------------------------------------------------------------------------------------------------------------
+// context / matrix objects behind the opaque C handles
+// ----------------------------------------------------------------------------------------------------------------
+struct hb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // legacy default stream unless hb_ctx_set_stream
+    int pointer_mode = HB_POINTER_HOST;
+    int num_sms = 148;
+    long long launches = 0;             // kernels launched through this context
+    // device scratch for deterministic two-stage reductions: partials + ticket counters
+    void *partials = nullptr;           // HB_PARTIAL_BYTES
+    unsigned int *tickets = nullptr;    // HB_NUM_TICKETS counters, zero between kernels
+    void *dscalars = nullptr;           // device scalar slots (alpha/beta staging, results)
+    void *hscalars = nullptr;           // pinned, device-mapped host page for scalar read-back
+    void *hscalars_dev = nullptr;       // device alias of hscalars
+    cudaEvent_t timer[2] = {nullptr, nullptr};
+};
+
+static constexpr size_t HB_PARTIAL_BYTES = 4u << 20;   // 4 MiB: (blocks x up-to-64 columns x 16 B) fits for grid <= 4096
+static constexpr int    HB_NUM_TICKETS   = 64;
+static constexpr size_t HB_SCALAR_BYTES  = 4096;
+static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids never exceed this
+
+struct hb_csr {
+    hb_ctx *ctx = nullptr;
+    int dtype = HB_F64;
+    int rows = 0, cols = 0, nnz = 0;
+    const int *pntr = nullptr, *indx = nullptr;
+    const void *vals = nullptr;
+    int variant = 0;                    // 0 auto
+    int max_row_nnz = 0;
+    double mean_row_nnz = 0;
+    int vec_aligned = 0;                // indx/vals 16-byte aligned -> 128-bit staging loads
+    int *stats_dev = nullptr;           // [0] = max row length (analysis kernel)
+};
+
+void hb_set_error(const std::string &msg);
+int  hb_cuda_fail(cudaError_t e, const char *what);
+
+#define HB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return hb_cuda_fail(e__, #call); } while (0)
+#define HB_ARG(cond, msg) do { if (!(cond)) { hb_set_error(std::string("invalid argument: ") + msg); return HB_ERR_ARG; } } while (0)
+#define HB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return hb_cuda_fail(e__, "kernel launch"); } while (0)
+
+static inline size_t hb_dtype_size(int dtype){ return dtype == HB_F32 ? 4 : dtype == HB_F64 ? 8 : dtype == HB_C32 ? 8 : 16; }
+static inline bool   hb_is_n(char t){ return t == 'N' || t == 'n'; }
+static inline bool   hb_is_c(char t){ return t == 'C' || t == 'c'; }
+
+// ----------------------------------------------------------------------------------------------------------------
+// scalar algebra: float, double, cplx<float>, cplx<double> (layout-compatible with std::complex / cuComplex)
+// ----------------------------------------------------------------------------------------------------------------
+template<typename R> struct __align__(2 * sizeof(R)) cplx { R re, im; };
+
+template<typename T> struct real_of            { using type = T; };
+template<typename R> struct real_of<cplx<R>>   { using type = R; };
+template<typename T> using real_t = typename real_of<T>::type;
+
+template<typename T> struct is_cplx            { static constexpr bool value = false; };
+template<typename R> struct is_cplx<cplx<R>>   { static constexpr bool value = true;  };
+
+template<typename T> __host__ __device__ __forceinline__ T zero_of(){ return T(0); }
+template<> __host__ __device__ __forceinline__ cplx<float>  zero_of<cplx<float>>(){ return {0.f, 0.f}; }
+template<> __host__ __device__ __forceinline__ cplx<double> zero_of<cplx<double>>(){ return {0.0, 0.0}; }
+template<typename T> __host__ __device__ __forceinline__ T one_of(){ return T(1); }
+template<> __host__ __device__ __forceinline__ cplx<float>  one_of<cplx<float>>(){ return {1.f, 0.f}; }
+template<> __host__ __device__ __forceinline__ cplx<double> one_of<cplx<double>>(){ return {1.0, 0.0}; }
+
+__host__ __device__ __forceinline__ float  hadd(float a, float b){ return a + b; }
+__host__ __device__ __forceinline__ double hadd(double a, double b){ return a + b; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hadd(cplx<R> a, cplx<R> b){ return {a.re + b.re, a.im + b.im}; }
+__host__ __device__ __forceinline__ float  hsub(float a, float b){ return a - b; }
+__host__ __device__ __forceinline__ double hsub(double a, double b){ return a - b; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hsub(cplx<R> a, cplx<R> b){ return {a.re - b.re, a.im - b.im}; }
+__host__ __device__ __forceinline__ float  hmul(float a, float b){ return a * b; }
+__host__ __device__ __forceinline__ double hmul(double a, double b){ return a * b; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hmul(cplx<R> a, cplx<R> b){
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+// acc + a*b
+__host__ __device__ __forceinline__ float  hfma(float a, float b, float c){ return fmaf(a, b, c); }
+__host__ __device__ __forceinline__ double hfma(double a, double b, double c){ return fma(a, b, c); }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hfma(cplx<R> a, cplx<R> b, cplx<R> c){
+    return {c.re + a.re * b.re - a.im * b.im, c.im + a.re * b.im + a.im * b.re};
+}
+__host__ __device__ __forceinline__ float  hconj(float a){ return a; }
+__host__ __device__ __forceinline__ double hconj(double a){ return a; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hconj(cplx<R> a){ return {a.re, -a.im}; }
+__host__ __device__ __forceinline__ float  hneg(float a){ return -a; }
+__host__ __device__ __forceinline__ double hneg(double a){ return -a; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hneg(cplx<R> a){ return {-a.re, -a.im}; }
+__host__ __device__ __forceinline__ float  hdiv(float a, float b){ return a / b; }
+__host__ __device__ __forceinline__ double hdiv(double a, double b){ return a / b; }
+template<typename R> __host__ __device__ __forceinline__ cplx<R> hdiv(cplx<R> a, cplx<R> b){
+    R d = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+__host__ __device__ __forceinline__ float  habs2(float a){ return a * a; }
+__host__ __device__ __forceinline__ double habs2(double a){ return a * a; }
+template<typename R> __host__ __device__ __forceinline__ R habs2(cplx<R> a){ return a.re * a.re + a.im * a.im; }
+__host__ __device__ __forceinline__ bool hiszero(float a){ return a == 0.f; }
+__host__ __device__ __forceinline__ bool hiszero(double a){ return a == 0.0; }
+template<typename R> __host__ __device__ __forceinline__ bool hiszero(cplx<R> a){ return a.re == R(0) && a.im == R(0); }
+__host__ __device__ __forceinline__ float  hreal(float a){ return a; }
+__host__ __device__ __forceinline__ double hreal(double a){ return a; }
+template<typename R> __host__ __device__ __forceinline__ R hreal(cplx<R> a){ return a.re; }
+template<typename T> __host__ __device__ __forceinline__ T from_real(real_t<T> r);
+template<> __host__ __device__ __forceinline__ float  from_real<float>(float r){ return r; }
+template<> __host__ __device__ __forceinline__ double from_real<double>(double r){ return r; }
+template<> __host__ __device__ __forceinline__ cplx<float>  from_real<cplx<float>>(float r){ return {r, 0.f}; }
+template<> __host__ __device__ __forceinline__ cplx<double> from_real<cplx<double>>(double r){ return {r, 0.0}; }
+
+// ----------------------------------------------------------------------------------------------------------------
+// loads: streaming (matrix data, touched once) vs cached read-only (x gather)
+// ----------------------------------------------------------------------------------------------------------------
+template<typename T> __device__ __forceinline__ T ld_stream(const T *p){ return __ldcs(p); }
+template<> __device__ __forceinline__ cplx<float> ld_stream<cplx<float>>(const cplx<float> *p){
+    float2 v = __ldcs(reinterpret_cast<const float2*>(p)); return {v.x, v.y};
+}
+template<> __device__ __forceinline__ cplx<double> ld_stream<cplx<double>>(const cplx<double> *p){
+    double2 v = __ldcs(reinterpret_cast<const double2*>(p)); return {v.x, v.y};
+}
+template<typename T> __device__ __forceinline__ T ld_ro(const T *p){ return __ldg(p); }
+template<> __device__ __forceinline__ cplx<float> ld_ro<cplx<float>>(const cplx<float> *p){
+    float2 v = __ldg(reinterpret_cast<const float2*>(p)); return {v.x, v.y};
+}
+template<> __device__ __forceinline__ cplx<double> ld_ro<cplx<double>>(const cplx<double> *p){
+    double2 v = __ldg(reinterpret_cast<const double2*>(p)); return {v.x, v.y};
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// reductions: warp shuffle -> shared -> one partial per block -> last block (ticket) sums the partials in
+// fixed order (deterministic; one atomic per block).
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float  shfl_down(float v, int d){ return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_down(double v, int d){ return __shfl_down_sync(0xffffffffu, v, d); }
+template<typename R> __device__ __forceinline__ cplx<R> shfl_down(cplx<R> v, int d){
+    return {shfl_down(v.re, d), shfl_down(v.im, d)};
+}
+template<typename T> __device__ __forceinline__ T warp_sum(T v){
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = hadd(v, shfl_down(v, d));
+    return v;
+}
+// block-wide sum; result valid in thread 0. `red` is shared scratch of >= 32 elements of T.
+template<typename T> __device__ __forceinline__ T block_sum(T v, T *red){
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    T r = zero_of<T>();
+    if (warp == 0){
+        r = (lane < nwarps) ? red[lane] : zero_of<T>();
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+// Called by all threads of a block after thread 0 holds the block's partial. Returns true (block-uniform) in the
+// LAST block to arrive; that block may then read partials[0..gridDim.x) — all of them are visible.
+__device__ __forceinline__ bool last_block_arrives(unsigned int *ticket){
+    __shared__ bool is_last;
+    __threadfence();
+    if (threadIdx.x == 0){
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0;               // re-arm for the next kernel on the stream
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+// fixed-order sum of `count` partials by one block; result valid in thread 0
+template<typename T> __device__ __forceinline__ T sum_partials(const volatile T *partials, int count, int stride, T *red){
+    T acc = zero_of<T>();
+    for (int i = threadIdx.x; i < count; i += blockDim.x){
+        const T *p = const_cast<const T*>(partials) + (size_t) i * stride;
+        acc = hadd(acc, __ldcg(reinterpret_cast<const T*>(p)));
+    }
+    return block_sum(acc, red);
+}
+template<> __device__ __forceinline__ cplx<float> sum_partials<cplx<float>>(const volatile cplx<float> *partials, int count, int stride, cplx<float> *red){
+    cplx<float> acc = zero_of<cplx<float>>();
+    for (int i = threadIdx.x; i < count; i += blockDim.x){
+        float2 v = __ldcg(reinterpret_cast<const float2*>(const_cast<const cplx<float>*>(partials) + (size_t) i * stride));
+        acc = hadd(acc, cplx<float>{v.x, v.y});
+    }
+    return block_sum(acc, red);
+}
+template<> __device__ __forceinline__ cplx<double> sum_partials<cplx<double>>(const volatile cplx<double> *partials, int count, int stride, cplx<double> *red){
+    cplx<double> acc = zero_of<cplx<double>>();
+    for (int i = threadIdx.x; i < count; i += blockDim.x){
+        double2 v = __ldcg(reinterpret_cast<const double2*>(const_cast<const cplx<double>*>(partials) + (size_t) i * stride));
+        acc = hadd(acc, cplx<double>{v.x, v.y});
+    }
+    return block_sum(acc, red);
+}
+
+// dtype dispatch on the host
+#define HB_DISPATCH(dtype, ...) \
+    switch (dtype) { \
+        case HB_F32: { using T = float;        __VA_ARGS__; break; } \
+        case HB_F64: { using T = double;       __VA_ARGS__; break; } \
+        case HB_C32: { using T = cplx<float>;  __VA_ARGS__; break; } \
+        case HB_C64: { using T = cplx<double>; __VA_ARGS__; break; } \
+        default: hb_set_error("unknown dtype"); return HB_ERR_ARG; }
+
+static inline int hb_grid_for(const hb_ctx *ctx, size_t work_items, int per_block, int blocks_per_sm){
+    size_t need = (work_items + per_block - 1) / per_block;
+    size_t cap = (size_t) ctx->num_sms * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+// scalar access helper: in host pointer mode the value is read on the host and passed by value;
+// in device pointer mode the kernel dereferences the device pointer.
+template<typename T> struct scalar_arg { T value; const T *dev; };
+template<typename T> static inline scalar_arg<T> make_scalar(const hb_ctx *ctx, const void *p){
+    scalar_arg<T> s; s.dev = nullptr; s.value = zero_of<T>();
+    if (ctx->pointer_mode == HB_POINTER_HOST) s.value = *reinterpret_cast<const T*>(p);
+    else s.dev = reinterpret_cast<const T*>(p);
+    return s;
+}
+template<typename T> __device__ __forceinline__ T get_scalar(const scalar_arg<T> &s){ return s.dev ? *s.dev : s.value; }

@@ -1,0 +1,152 @@
+// hb_context.cu — context, error plumbing and device memory of libhalab200.
+// Replaces: gpu_engine handle management (reference gpu/hala_gpu_engine.hpp:60-163), gpu_allocate/gpu_free/gpu_copy_n
+// (gpu/hala_cuda_common.hpp:253-330), gpu_vector::fill (gpu/hala_gpu_vector.hpp:147-156), set_zero (gpu_engine.hpp:335-352).
+#include "hb_common.cuh"
+
+static thread_local std::string g_last_error;
+
+void hb_set_error(const std::string &msg){ g_last_error = msg; }
+int hb_cuda_fail(cudaError_t e, const char *what){
+    g_last_error = std::string(what) + " failed with message: " + cudaGetErrorString(e);
+    return HB_ERR_CUDA;
+}
+
+template<typename T> __global__ void fill_kernel(size_t n, T value, T *x){
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) x[i] = value;
+}
+
+extern "C" {
+
+const char* hb_version(void){ return "halab200 0.1 (sm_100a)"; }
+const char* hb_last_error(void){ return g_last_error.c_str(); }
+
+int hb_device_count(int *count){
+    HB_ARG(count, "count is null");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess){ *count = 0; cudaGetLastError(); }
+    return HB_OK;
+}
+
+int hb_ctx_create(int device, hb_ctx **out){
+    HB_ARG(out, "ctx output is null");
+    int n = 0;
+    HB_CUDA(cudaGetDeviceCount(&n));
+    HB_ARG(device >= 0 && device < n, "device id out of range");
+    HB_CUDA(cudaSetDevice(device));
+    hb_ctx *ctx = new hb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    HB_CUDA(cudaMalloc(&ctx->partials, HB_PARTIAL_BYTES));
+    HB_CUDA(cudaMalloc((void**) &ctx->tickets, HB_NUM_TICKETS * sizeof(unsigned int)));
+    HB_CUDA(cudaMemset(ctx->tickets, 0, HB_NUM_TICKETS * sizeof(unsigned int)));
+    HB_CUDA(cudaMalloc(&ctx->dscalars, HB_SCALAR_BYTES));
+    HB_CUDA(cudaMemset(ctx->dscalars, 0, HB_SCALAR_BYTES));
+    HB_CUDA(cudaHostAlloc(&ctx->hscalars, HB_SCALAR_BYTES, cudaHostAllocMapped));
+    memset(ctx->hscalars, 0, HB_SCALAR_BYTES);
+    HB_CUDA(cudaHostGetDevicePointer(&ctx->hscalars_dev, ctx->hscalars, 0));
+    HB_CUDA(cudaEventCreate(&ctx->timer[0]));
+    HB_CUDA(cudaEventCreate(&ctx->timer[1]));
+    *out = ctx;
+    return HB_OK;
+}
+
+int hb_ctx_destroy(hb_ctx *ctx){
+    if (!ctx) return HB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->timer[0]) cudaEventDestroy(ctx->timer[0]);
+    if (ctx->timer[1]) cudaEventDestroy(ctx->timer[1]);
+    cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->dscalars); cudaFreeHost(ctx->hscalars);
+    delete ctx;
+    return HB_OK;
+}
+
+int hb_ctx_device(const hb_ctx *ctx, int *device){ HB_ARG(ctx && device, "null"); *device = ctx->device; return HB_OK; }
+int hb_ctx_set_stream(hb_ctx *ctx, void *s){ HB_ARG(ctx, "ctx is null"); ctx->stream = (cudaStream_t) s; return HB_OK; }
+int hb_ctx_get_stream(const hb_ctx *ctx, void **s){ HB_ARG(ctx && s, "null"); *s = (void*) ctx->stream; return HB_OK; }
+int hb_ctx_sync(hb_ctx *ctx){
+    HB_ARG(ctx, "ctx is null");
+    HB_CUDA(cudaSetDevice(ctx->device));
+    HB_CUDA(cudaDeviceSynchronize());
+    return HB_OK;
+}
+int hb_ctx_set_pointer_mode(hb_ctx *ctx, int mode){
+    HB_ARG(ctx, "ctx is null");
+    HB_ARG(mode == HB_POINTER_HOST || mode == HB_POINTER_DEVICE, "pointer mode");
+    ctx->pointer_mode = mode;
+    return HB_OK;
+}
+int hb_ctx_get_pointer_mode(const hb_ctx *ctx, int *mode){ HB_ARG(ctx && mode, "null"); *mode = ctx->pointer_mode; return HB_OK; }
+int hb_ctx_launch_count(const hb_ctx *ctx, long long *count){ HB_ARG(ctx && count, "null"); *count = ctx->launches; return HB_OK; }
+
+int hb_timer_start(hb_ctx *ctx){
+    HB_ARG(ctx, "ctx is null");
+    HB_CUDA(cudaEventRecord(ctx->timer[0], ctx->stream));
+    return HB_OK;
+}
+int hb_timer_stop(hb_ctx *ctx, float *ms){
+    HB_ARG(ctx && ms, "null");
+    HB_CUDA(cudaEventRecord(ctx->timer[1], ctx->stream));
+    HB_CUDA(cudaEventSynchronize(ctx->timer[1]));
+    HB_CUDA(cudaEventElapsedTime(ms, ctx->timer[0], ctx->timer[1]));
+    return HB_OK;
+}
+
+int hb_malloc(hb_ctx *ctx, size_t bytes, void **ptr){
+    HB_ARG(ctx && ptr, "null");
+    HB_CUDA(cudaSetDevice(ctx->device));      // as gpu_allocate does (gpu/hala_cuda_common.hpp:255)
+    *ptr = nullptr;
+    if (bytes == 0) return HB_OK;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess){ hb_cuda_fail(e, "hb_malloc"); return HB_ERR_ALLOC; }
+    return HB_OK;
+}
+int hb_free(hb_ctx *ctx, void *ptr){
+    (void) ctx;
+    if (ptr) HB_CUDA(cudaFree(ptr));
+    return HB_OK;
+}
+static cudaMemcpyKind to_kind(int kind){
+    return kind == HB_H2D ? cudaMemcpyHostToDevice : kind == HB_D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+}
+int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind){
+    HB_ARG(ctx, "ctx is null");
+    if (bytes == 0) return HB_OK;
+    HB_CUDA(cudaMemcpyAsync(dst, src, bytes, to_kind(kind), ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+int hb_memcpy_async(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind){
+    HB_ARG(ctx, "ctx is null");
+    if (bytes == 0) return HB_OK;
+    HB_CUDA(cudaMemcpyAsync(dst, src, bytes, to_kind(kind), ctx->stream));
+    return HB_OK;
+}
+int hb_memset_zero(hb_ctx *ctx, void *ptr, size_t bytes){
+    HB_ARG(ctx, "ctx is null");
+    if (bytes == 0) return HB_OK;
+    HB_CUDA(cudaMemsetAsync(ptr, 0, bytes, ctx->stream));
+    return HB_OK;
+}
+int hb_fill(hb_ctx *ctx, int dtype, size_t n, const void *host_value, void *x){
+    HB_ARG(ctx && host_value, "null");
+    if (n == 0) return HB_OK;
+    HB_ARG(x, "x is null");
+    int grid = hb_grid_for(ctx, n, 1024, 8);
+    if (dtype == -1){
+        fill_kernel<int><<<grid, 256, 0, ctx->stream>>>(n, *(const int*) host_value, (int*) x);
+    }else{
+        HB_DISPATCH(dtype, (fill_kernel<T><<<grid, 256, 0, ctx->stream>>>(n, *(const T*) host_value, (T*) x)));
+    }
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_host_alloc(size_t bytes, void **ptr){
+    HB_ARG(ptr, "null");
+    HB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return HB_OK;
+}
+int hb_host_free(void *ptr){ if (ptr) HB_CUDA(cudaFreeHost(ptr)); return HB_OK; }
+
+}

@@ -1,0 +1,428 @@
+// hb_krylov.cu — fused vector kernels of the CG / GMRES iterations and the tall-skinny gemv pair.
+// Replaces, per CG iteration, cublas?axpy x2 + cublas?nrm2 + cublas?copy + cublas?dot + cublas?scal + cublas?axpy
+// (reference hex/solvers/hala_solvers_cg.hpp:135-150 through gpu/hala_gpu_blas1.hpp) by two streaming passes, and per
+// GMRES inner iteration cublas?gemv('T') + cublas?gemv('N') + cublas?nrm2 (hala_solvers_gmres.hpp:67-72,192 through
+// gpu/hala_gpu_blas2.hpp:39-62) by one multi-dot pass and one multi-axpy+norm pass over the Krylov basis.
+// Every scalar these kernels consume or produce lives in device memory; nothing here synchronises with the host.
+#include "hb_common.cuh"
+
+static constexpr int KR_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------ CG state (device)
+// zr[2] is double-buffered by iteration parity so that no kernel both reads and writes the same scalar.
+template<typename T> struct cg_state {
+    T zr[2];            // <r, z> of the current / next iteration (z == r: identity preconditioner)
+    T pAp;              // <p, A p>
+    double rnorm;       // ||r||_2 after the last update
+    double tol;
+    int iterations;     // operator applications so far (reference counter, starts at 1)
+    int max_iter;
+    int done;           // set by the update kernel when the reference's stop test fires
+    int pad;
+};
+struct cg_host_status { volatile int done; volatile int iterations; volatile double rnorm; };
+
+// x += a p ; r -= a q ; rr = <r, r> ; then (last block) bookkeeping of solve_cg_core:  iterations, stop test, zr_next
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) cg_update_kernel(int n, cg_state<T> *st, int parity, const T * __restrict__ p, const T * __restrict__ q,
+                                                               T *x, T *r, void *partials_v, unsigned int *ticket, cg_host_status *host){
+    __shared__ double red[32];
+    if (st->done) return;
+    const T a = hdiv(st->zr[parity], st->pAp);
+    const T na = hneg(a);
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
+        x[i] = hfma(a, p[i], x[i]);
+        T ri = hfma(na, q[i], r[i]);
+        r[i] = ri;
+        acc += (double) habs2(ri);
+    }
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double b = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0){
+            st->zr[parity ^ 1] = from_real<T>((real_t<T>) rr);
+            const double nrm = sqrt(rr);
+            st->rnorm = nrm;
+            const int it = st->iterations + 1;  // iterations++ of solve_cg_core: one more operator application
+            st->iterations = it;
+            // reference test: (it == max_iter) || (nrm < tol).  >= is identical for max_iter >= 2 and also terminates for
+            // max_iter < 2 (where the reference would spin); a NaN residual stops as well instead of iterating forever.
+            const int stop = (it >= st->max_iter) || (nrm < st->tol) || !(nrm == nrm);
+            if (stop) st->done = 1;
+            if (host){ host->rnorm = nrm; host->iterations = it; __threadfence_system(); if (stop) host->done = 1; }
+        }
+    }
+}
+// p = r + (zr_next / zr) p
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) cg_direction_kernel(int n, const cg_state<T> *st, int parity, const T * __restrict__ r, T *p){
+    if (st->done) return;
+    const T beta = hdiv(st->zr[parity ^ 1], st->zr[parity]);
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride)
+        p[i] = hfma(beta, p[i], r[i]);
+}
+
+// setup: r = b - q (q = A x0), p = r, zr[0] = <r,r>; state initialised by the last block
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) cg_setup_kernel(int n, cg_state<T> *st, double tol, int max_iter, const T * __restrict__ b,
+                                                              const T * __restrict__ q, T *r, T *p, void *partials_v, unsigned int *ticket,
+                                                              cg_host_status *host){
+    __shared__ double red[32];
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
+        T ri = hsub(b[i], q[i]);
+        r[i] = ri; p[i] = ri;
+        acc += (double) habs2(ri);
+    }
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double bs = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0){
+            st->zr[0] = from_real<T>((real_t<T>) rr); st->zr[1] = zero_of<T>(); st->pAp = one_of<T>();
+            st->rnorm = sqrt(rr); st->tol = tol; st->iterations = 1; st->max_iter = max_iter; st->done = 0; st->pad = 0;
+            if (host){ host->rnorm = sqrt(rr); host->iterations = 1; host->done = 0; __threadfence_system(); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generic fused pieces (C ABI)
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) axpy2_nrm2_kernel(int n, const T *a_dev, const T * __restrict__ p, const T * __restrict__ q,
+                                                                T *x, T *r, void *partials_v, unsigned int *ticket, T *rr_dev){
+    __shared__ double red[32];
+    const T a = *a_dev, na = hneg(a);
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
+        x[i] = hfma(a, p[i], x[i]);
+        T ri = hfma(na, q[i], r[i]);
+        r[i] = ri;
+        acc += (double) habs2(ri);
+    }
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double b = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0) *rr_dev = from_real<T>((real_t<T>) rr);
+    }
+}
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) xpby_kernel(int n, const T * __restrict__ r, const T *b_dev, T *p){
+    const T beta = *b_dev;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride)
+        p[i] = hfma(beta, p[i], r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ GMRES: multi-dot
+// h[c] = sum_i op(W[i,c]) r[i] for c < k in ONE pass: each thread keeps RPT rows of r in registers and walks the k
+// columns; per column a warp-shuffle reduction feeds a per-warp shared accumulator, so r is read once and every column
+// of W once.  Block partials -> last block sums them in fixed order.
+static constexpr int MD_RPT  = 4;          // rows per thread per sweep
+static constexpr int MD_KMAX = 64;         // columns handled per launch (restart <= 64 in one launch; more -> several launches)
+
+template<typename T, bool CONJ>
+__global__ void __launch_bounds__(KR_THREADS) multi_dot_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T * __restrict__ r,
+                                                               void *partials_v, unsigned int *ticket, T *h_out, const int *skip_flag){
+    __shared__ T acc[MD_KMAX][KR_THREADS / 32];
+    __shared__ T red[32];
+    if (skip_flag && *skip_flag) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < MD_KMAX * (KR_THREADS / 32); c += blockDim.x) (&acc[0][0])[c] = zero_of<T>();
+    __syncthreads();
+    const long long sweep = (long long) gridDim.x * KR_THREADS * MD_RPT;
+    for (long long base = (long long) blockIdx.x * KR_THREADS * MD_RPT; base < rows; base += sweep){
+        T rv[MD_RPT]; long long idx[MD_RPT];
+        #pragma unroll
+        for (int u = 0; u < MD_RPT; u++){
+            idx[u] = base + (long long) u * KR_THREADS + threadIdx.x;
+            rv[u] = (idx[u] < rows) ? r[idx[u]] : zero_of<T>();
+        }
+        for (int c = 0; c < k; c++){
+            const T *col = W + (size_t) c * ldw;
+            T w[MD_RPT];
+            #pragma unroll
+            for (int u = 0; u < MD_RPT; u++) w[u] = (idx[u] < rows) ? ld_stream(col + idx[u]) : zero_of<T>();
+            T part = zero_of<T>();
+            #pragma unroll
+            for (int u = 0; u < MD_RPT; u++) part = hfma(CONJ ? hconj(w[u]) : w[u], rv[u], part);
+            part = warp_sum(part);
+            if (lane == 0) acc[c][warp] = hadd(acc[c][warp], part);
+        }
+    }
+    __syncthreads();
+    T *partials = reinterpret_cast<T*>(partials_v);     // layout [block][k]
+    for (int c = threadIdx.x; c < k; c += blockDim.x){
+        T s = zero_of<T>();
+        #pragma unroll
+        for (int w = 0; w < KR_THREADS / 32; w++) s = hadd(s, acc[c][w]);
+        partials[(size_t) blockIdx.x * k + c] = s;
+    }
+    if (last_block_arrives(ticket)){
+        for (int c = 0; c < k; c++){
+            T total = sum_partials<T>(partials + c, gridDim.x, k, red);
+            if (threadIdx.x == 0) h_out[c] = total;
+        }
+    }
+}
+
+// r -= W h ; nrm2sq = sum |r_i|^2 of the updated r (same pass). h (k scalars) is read from device memory into shared.
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) multi_axpy_nrm2_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T *h_dev,
+                                                                     T *r, void *partials_v, unsigned int *ticket, T *nrm2sq_out, const int *skip_flag,
+                                                                     T scale_h){
+    __shared__ T h[MD_KMAX];
+    __shared__ double red[32];
+    if (skip_flag && *skip_flag) return;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) h[c] = hmul(scale_h, h_dev[c]);
+    __syncthreads();
+    double acc = 0.0;
+    const long long sweep = (long long) gridDim.x * KR_THREADS * 2;
+    for (long long base = (long long) blockIdx.x * KR_THREADS * 2; base < rows; base += sweep){
+        const long long i0 = base + threadIdx.x, i1 = i0 + KR_THREADS;
+        T t0 = (i0 < rows) ? r[i0] : zero_of<T>(), t1 = (i1 < rows) ? r[i1] : zero_of<T>();
+        #pragma unroll 4
+        for (int c = 0; c < k; c++){
+            const T *col = W + (size_t) c * ldw;
+            T w0 = (i0 < rows) ? ld_stream(col + i0) : zero_of<T>();
+            T w1 = (i1 < rows) ? ld_stream(col + i1) : zero_of<T>();
+            t0 = hfma(w0, h[c], t0); t1 = hfma(w1, h[c], t1);
+        }
+        if (i0 < rows){ r[i0] = t0; acc += (double) habs2(t0); }
+        if (i1 < rows){ r[i1] = t1; acc += (double) habs2(t1); }
+    }
+    if (nrm2sq_out){
+        double *partials = reinterpret_cast<double*>(partials_v);
+        double b = block_sum(acc, red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = b;
+        if (last_block_arrives(ticket)){
+            double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+            if (threadIdx.x == 0) *nrm2sq_out = from_real<T>((real_t<T>) rr);
+        }
+    }
+}
+
+// w_out = r / sqrt(real(*nrm2sq_dev))   (normalise + append to the basis in one pass; also rewrites r when r_out != null)
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) scale_copy_kernel(long long rows, const T * __restrict__ r, const T *nrm2sq_dev, T *w_out, T *r_out){
+    const real_t<T> inv = real_t<T>(1) / (real_t<T>) sqrt((double) hreal(*nrm2sq_dev));
+    const T s = from_real<T>(inv);
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) rows; i += stride){
+        T v = hmul(s, r[i]);
+        w_out[i] = v;
+        if (r_out) r_out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ general gemv (column-major)
+// 'N': y = alpha A x + beta y  — one thread per row (coalesced over the column-major A), any strides
+template<typename T>
+__global__ void __launch_bounds__(KR_THREADS) gemv_n_kernel(int M, int N, scalar_arg<T> alpha_s, const T * __restrict__ A, size_t lda,
+                                                            const T * __restrict__ x, long long incx, scalar_arg<T> beta_s, T *y, long long incy){
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < M; i += (long long) gridDim.x * blockDim.x){
+        T sum = zero_of<T>();
+        #pragma unroll 4
+        for (int c = 0; c < N; c++) sum = hfma(A[(size_t) c * lda + i], x[c * incx], sum);
+        T out = hmul(alpha, sum);
+        if (use_beta) out = hfma(beta, y[i * incy], out);
+        y[i * incy] = out;
+    }
+}
+// 'T'/'C' finishing step after multi_dot produced raw sums in tmp: y[c] = alpha * tmp[c] + beta * y[c]
+template<typename T>
+__global__ void gemv_t_finish_kernel(int N, scalar_arg<T> alpha_s, const T *tmp, scalar_arg<T> beta_s, T *y, long long incy){
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x){
+        T out = hmul(alpha, tmp[c]);
+        if (use_beta) out = hfma(beta, y[c * incy], out);
+        y[c * incy] = out;
+    }
+}
+// 'T'/'C' with a strided x: one block per column (rare path: only the strided BLAS tests reach it)
+template<typename T, bool CONJ>
+__global__ void __launch_bounds__(KR_THREADS) gemv_t_strided_kernel(int M, int N, scalar_arg<T> alpha_s, const T * __restrict__ A, size_t lda,
+                                                                    const T * __restrict__ x, long long incx, scalar_arg<T> beta_s, T *y, long long incy){
+    __shared__ T red[32];
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    for (int c = blockIdx.x; c < N; c += gridDim.x){
+        T sum = zero_of<T>();
+        for (int i = threadIdx.x; i < M; i += blockDim.x){
+            T a = A[(size_t) c * lda + i];
+            sum = hfma(CONJ ? hconj(a) : a, x[i * incx], sum);
+        }
+        sum = block_sum(sum, red);
+        if (threadIdx.x == 0){
+            T out = hmul(alpha, sum);
+            if (use_beta) out = hfma(beta, y[c * incy], out);
+            y[c * incy] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ internal launchers (used by hb_solvers.cu)
+static inline int kr_grid(const hb_ctx *ctx, long long n, int per_block){
+    long long need = (n + per_block - 1) / per_block;
+    long long cap = (long long) ctx->num_sms * 4;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int k, const void *W, size_t ldw, const void *r, void *h_dev, const int *skip){
+    for (int c0 = 0; c0 < k; c0 += MD_KMAX){
+        const int kk = (k - c0 < MD_KMAX) ? (k - c0) : MD_KMAX;
+        int grid = kr_grid(ctx, rows, KR_THREADS * MD_RPT);
+        HB_DISPATCH(dtype, {
+            const T *Wc = (const T*) W + (size_t) c0 * ldw;
+            T *hc = (T*) h_dev + c0;
+            if (conj && is_cplx<T>::value)
+                multi_dot_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip);
+            else
+                multi_dot_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip);
+        });
+        HB_LAUNCH_CHECK(ctx);
+    }
+    return HB_OK;
+}
+
+// r += scale * W h  (scale = -1 for the projection, +1 for krylov_combine); optional |r|^2 of the result
+int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const void *W, size_t ldw, const void *h_dev, void *r,
+                           void *nrm2sq_dev, double scale, const int *skip){
+    for (int c0 = 0; c0 < k; c0 += MD_KMAX){
+        const int kk = (k - c0 < MD_KMAX) ? (k - c0) : MD_KMAX;
+        const bool last = (c0 + kk >= k);
+        int grid = kr_grid(ctx, rows, KR_THREADS * 2);
+        HB_DISPATCH(dtype, {
+            multi_axpy_nrm2_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, (const T*) W + (size_t) c0 * ldw, ldw, (const T*) h_dev + c0,
+                (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));
+        });
+        HB_LAUNCH_CHECK(ctx);
+    }
+    return HB_OK;
+}
+
+int hb_scale_copy_internal(hb_ctx *ctx, int dtype, long long rows, const void *r, const void *nrm2sq_dev, void *w_out, void *r_out){
+    int grid = kr_grid(ctx, rows, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (scale_copy_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, (const T*) r, (const T*) nrm2sq_dev, (T*) w_out, (T*) r_out)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+
+// CG kernels, typed entry points
+int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol, int max_iter, const void *b, const void *q, void *r, void *p, void *host){
+    int grid = kr_grid(ctx, n, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (cg_setup_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, tol, max_iter, (const T*) b, (const T*) q,
+                        (T*) r, (T*) p, ctx->partials, ctx->tickets + 4, (cg_host_status*) host)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *p, const void *q, void *x, void *r, void *host){
+    int grid = kr_grid(ctx, n, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (cg_update_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) p, (const T*) q,
+                        (T*) x, (T*) r, ctx->partials, ctx->tickets + 4, (cg_host_status*) host)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, const void *r, void *p){
+    int grid = kr_grid(ctx, n, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (cg_direction_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const cg_state<T>*) state, parity, (const T*) r, (T*) p)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+size_t hb_cg_state_bytes(int dtype){
+    switch (dtype){ case HB_F32: return sizeof(cg_state<float>); case HB_F64: return sizeof(cg_state<double>);
+                    case HB_C32: return sizeof(cg_state<cplx<float>>); default: return sizeof(cg_state<cplx<double>>); }
+}
+size_t hb_cg_state_pap_offset(int dtype){
+    switch (dtype){ case HB_F32: return offsetof(cg_state<float>, pAp); case HB_F64: return offsetof(cg_state<double>, pAp);
+                    case HB_C32: return offsetof(cg_state<cplx<float>>, pAp); default: return offsetof(cg_state<cplx<double>>, pAp); }
+}
+size_t hb_cg_state_done_offset(int dtype){
+    switch (dtype){ case HB_F32: return offsetof(cg_state<float>, done); case HB_F64: return offsetof(cg_state<double>, done);
+                    case HB_C32: return offsetof(cg_state<cplx<float>>, done); default: return offsetof(cg_state<cplx<double>>, done); }
+}
+
+extern "C" {
+
+int hb_multi_dot(hb_ctx *ctx, int dtype, int conj, int rows, int k, const void *W, size_t ldw, const void *r, void *h_dev){
+    HB_ARG(ctx && h_dev, "null");
+    HB_ARG(rows >= 0 && k >= 0, "negative size");
+    if (k == 0) return HB_OK;
+    HB_ARG(rows == 0 || (W && r), "null array");
+    return hb_multi_dot_internal(ctx, dtype, conj, rows, k, W, ldw, r, h_dev, nullptr);
+}
+int hb_multi_axpy_nrm2(hb_ctx *ctx, int dtype, int rows, int k, const void *W, size_t ldw, const void *h_dev, void *r, void *nrm2sq_dev){
+    HB_ARG(ctx, "null");
+    HB_ARG(rows >= 0 && k >= 0, "negative size");
+    HB_ARG(k == 0 || (W && h_dev), "null array");
+    if (k == 0){
+        // nothing to subtract: still deliver the norm
+        if (nrm2sq_dev) return hb_multi_axpy_internal(ctx, dtype, rows, 0, r, 0, r, r, nrm2sq_dev, -1.0, nullptr);
+        return HB_OK;
+    }
+    return hb_multi_axpy_internal(ctx, dtype, rows, k, W, ldw, h_dev, r, nrm2sq_dev, -1.0, nullptr);
+}
+int hb_axpy2_nrm2(hb_ctx *ctx, int dtype, int n, const void *a_dev, const void *p, const void *q, void *x, void *r, void *rr_dev){
+    HB_ARG(ctx && a_dev && rr_dev, "null");
+    HB_ARG(n >= 0, "negative size");
+    int grid = kr_grid(ctx, n, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (axpy2_nrm2_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) a_dev, (const T*) p, (const T*) q, (T*) x, (T*) r,
+                        ctx->partials, ctx->tickets + 5, (T*) rr_dev)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_xpby(hb_ctx *ctx, int dtype, int n, const void *r, const void *b_dev, void *p){
+    HB_ARG(ctx && b_dev, "null");
+    if (n <= 0) return HB_OK;
+    int grid = kr_grid(ctx, n, KR_THREADS * 4);
+    HB_DISPATCH(dtype, (xpby_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) r, (const T*) b_dev, (T*) p)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+
+int hb_gemv(hb_ctx *ctx, int dtype, char trans, int M, int N, const void *alpha, const void *A, int lda,
+            const void *x, int incx, const void *beta, void *y, int incy){
+    HB_ARG(ctx && alpha && beta, "null");
+    HB_ARG(M >= 0 && N >= 0 && lda >= (M > 1 ? M : 1), "bad dimensions");
+    const int ny = hb_is_n(trans) ? M : N;
+    if (ny == 0) return HB_OK;
+    HB_DISPATCH(dtype, {
+        scalar_arg<T> a = make_scalar<T>(ctx, alpha), b = make_scalar<T>(ctx, beta);
+        if (hb_is_n(trans)){
+            int grid = kr_grid(ctx, M, KR_THREADS);
+            gemv_n_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(M, N, a, (const T*) A, (size_t) lda, (const T*) x, incx, b, (T*) y, incy);
+            HB_LAUNCH_CHECK(ctx);
+        }else{
+            const bool cj = hb_is_c(trans) && is_cplx<T>::value;
+            if (incx == 1 && N <= 1024 && M > 0){
+                // tall-skinny: fused multi-dot over the columns, then the alpha/beta finish
+                T *tmp = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->partials) + HB_PARTIAL_BYTES - 1024 * sizeof(T));
+                int rc = hb_multi_dot_internal(ctx, dtype, cj ? 1 : 0, M, N, A, (size_t) lda, x, tmp, nullptr);
+                if (rc != HB_OK) return rc;
+                gemv_t_finish_kernel<T><<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, a, tmp, b, (T*) y, incy);
+                HB_LAUNCH_CHECK(ctx);
+            }else{
+                int grid = N < ctx->num_sms * 4 ? N : ctx->num_sms * 4;
+                if (cj) gemv_t_strided_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(M, N, a, (const T*) A, (size_t) lda, (const T*) x, incx, b, (T*) y, incy);
+                else    gemv_t_strided_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(M, N, a, (const T*) A, (size_t) lda, (const T*) x, incx, b, (T*) y, incy);
+                HB_LAUNCH_CHECK(ctx);
+            }
+        }
+    });
+    return HB_OK;
+}
+
+}

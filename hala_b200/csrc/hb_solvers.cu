@@ -1,0 +1,234 @@
+// hb_solvers.cu — CG and GMRES with the iteration on the device.
+// hb_cg   : recurrence / counter / stop test of solve_cg_core (reference hex/solvers/hala_solvers_cg.hpp:92-156, wired as
+//           :181-227 with the identity preconditioner), three kernels per iteration (SpMV+<p,Ap>, x/r update+||r||^2,
+//           direction update), all scalars device-resident; the host only enqueues batches and polls a mapped flag.
+// hb_gmres: solve_gmres (hex/solvers/hala_solvers_gmres.hpp:127-230): SpMV, fused multi-dot + multi-axpy+norm as the
+//           classical Gram-Schmidt step, Givens QR of the Hessenberg matrix on the host (k+2 scalars cross PCIe per inner
+//           iteration, once), packed back-substitution and the basis combination.
+#include "hb_common.cuh"
+#include <vector>
+#include <cmath>
+
+int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
+int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
+int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int k, const void *W, size_t ldw, const void *r, void *h_dev, const int *skip);
+int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const void *W, size_t ldw, const void *h_dev, void *r,
+                           void *nrm2sq_dev, double scale, const int *skip);
+int hb_scale_copy_internal(hb_ctx *ctx, int dtype, long long rows, const void *r, const void *nrm2sq_dev, void *w_out, void *r_out);
+int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol, int max_iter, const void *b, const void *q, void *r, void *p, void *host);
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *p, const void *q, void *x, void *r, void *host);
+int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, const void *r, void *p);
+size_t hb_cg_state_bytes(int dtype);
+size_t hb_cg_state_pap_offset(int dtype);
+size_t hb_cg_state_done_offset(int dtype);
+
+struct cg_host_status_h { volatile int done; volatile int iterations; volatile double rnorm; };
+
+namespace {
+
+struct dev_buffer {
+    void *p = nullptr;
+    ~dev_buffer(){ if (p) cudaFree(p); }
+    int alloc(size_t bytes){
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e != cudaSuccess){ hb_cuda_fail(e, "solver workspace cudaMalloc"); return HB_ERR_ALLOC; }
+        return HB_OK;
+    }
+};
+struct event_pair {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~event_pair(){ for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+
+// ---- host-side Givens / packed triangular solve in the matrix's own scalar type (netlib ?rotg / ?rot / ?tpsv) ----
+template<typename T> inline real_t<T> habs(T a){ return std::sqrt(habs2(a)); }
+inline float  habs(float a){ return std::fabs(a); }
+inline double habs(double a){ return std::fabs(a); }
+
+template<typename R> void h_rotg(R &a, R &b, R &c, R &s){
+    R roe = b, absa = std::fabs(a), absb = std::fabs(b);
+    if (absa > absb) roe = a;
+    R scale = absa + absb;
+    if (scale == R(0)){ c = 1; s = 0; a = 0; b = 0; return; }
+    R r = scale * std::sqrt((a / scale) * (a / scale) + (b / scale) * (b / scale));
+    if (roe < 0) r = -r;
+    c = a / r; s = b / r;
+    R z = 1;
+    if (absa > absb) z = s;
+    if (absb >= absa && c != R(0)) z = R(1) / c;
+    a = r; b = z;
+}
+template<typename R> void h_rotg(cplx<R> &a, cplx<R> &b, R &c, cplx<R> &s){
+    R absa = habs(a);
+    if (absa == R(0)){ c = 0; s = {R(1), R(0)}; a = b; return; }
+    R scale = absa + habs(b);
+    cplx<R> as = {a.re / scale, a.im / scale}, bs = {b.re / scale, b.im / scale};
+    R norm = scale * std::sqrt(habs2(as) + habs2(bs));
+    cplx<R> alpha = {a.re / absa, a.im / absa};
+    c = absa / norm;
+    cplx<R> t = hmul(alpha, hconj(b));
+    s = {t.re / norm, t.im / norm};
+    a = {alpha.re * norm, alpha.im * norm};
+}
+// x' = c x + s y ; y' = c y - conj(s) x
+template<typename T> void h_rot(T &x, T &y, real_t<T> c, T s){
+    T cc = from_real<T>(c);
+    T tx = hadd(hmul(cc, x), hmul(s, y));
+    y = hsub(hmul(cc, y), hmul(hconj(s), x));
+    x = tx;
+}
+template<typename T> void h_tpsv_unn(int n, const std::vector<T> &ap, std::vector<T> &x){
+    size_t kk = (size_t) n * (n + 1) / 2;
+    for (int j = n - 1; j >= 0; j--){
+        size_t diag = kk - 1;
+        if (!hiszero(x[j])){
+            x[j] = hdiv(x[j], ap[diag]);
+            T t = x[j];
+            size_t k = diag - 1;
+            for (int i = j - 1; i >= 0; i--, k--) x[i] = hsub(x[i], hmul(t, ap[k]));
+        }
+        kk -= (size_t) j + 1;
+    }
+}
+
+template<typename T>
+int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, int max_outer, int restart, int cproj, int *iters, double *res){
+    using R = real_t<T>;
+    const int n = A->rows;
+    const R tol = (R) tol_d;
+    dev_buffer tbuf, wbuf, hbuf;
+    int rc;
+    if ((rc = tbuf.alloc(sizeof(T) * (size_t) n)) != HB_OK) return rc;
+    if ((rc = wbuf.alloc(sizeof(T) * (size_t) n * (size_t) restart)) != HB_OK) return rc;
+    if ((rc = hbuf.alloc(sizeof(T) * (size_t) (restart + 2))) != HB_OK) return rc;
+    T *t = (T*) tbuf.p, *W = (T*) wbuf.p, *hdev = (T*) hbuf.p;
+    T *hhost = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->hscalars) + 1024);   // pinned staging, (restart+2) scalars <= 3 KiB
+    HB_ARG((size_t) (restart + 2) * sizeof(T) <= HB_SCALAR_BYTES - 1024, "restart too large for the pinned staging area (max 190)");
+    const int saved_mode = ctx->pointer_mode;
+    ctx->pointer_mode = HB_POINTER_HOST;
+    struct restore { hb_ctx *c; int m; ~restore(){ c->pointer_mode = m; } } restore_mode{ctx, saved_mode};
+
+    std::vector<T> H, S, Z, coeffs;
+    std::vector<R> C;
+    H.reserve((size_t) restart * (restart + 1)); S.reserve(restart + 1); C.reserve(restart + 1); Z.reserve(restart + 1);
+    R inner_res = 0, outer_res = tol + R(1);
+    int total = 0, outer = 0;
+    const T one = one_of<T>(), mone = hneg(one);
+
+    while ((outer_res > tol) && (outer < max_outer)){
+        H.clear(); S.clear(); C.clear(); Z.clear();
+        // t = b - A x ; r = P^-1 t (identity) ; inner_res = ||r|| ; W[:,0] = r / ||r||
+        HB_CUDA(cudaMemcpyAsync(t, b, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = hb_spmv(ctx, A, 'N', &mone, x, &one, t)) != HB_OK) return rc;
+        total++;
+        if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, 0, t, 0, t, t, hdev, -1.0, nullptr)) != HB_OK) return rc;     // hdev[0] = ||t||^2
+        if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev, W, nullptr)) != HB_OK) return rc;
+        HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CUDA(cudaStreamSynchronize(ctx->stream));
+        inner_res = (R) std::sqrt((double) hreal(hhost[0]));
+        Z.push_back(from_real<T>(inner_res));
+
+        int inner = 0;
+        while ((inner_res > tol) && (inner < restart)){
+            const T *wj = W + (size_t) inner * n;
+            if ((rc = hb_spmv_internal(ctx, A, wj, t, nullptr)) != HB_OK) return rc;                         // t = A w_j ; r = P^-1 t
+            total++;
+            const int k = inner + 1;
+            if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, (size_t) n, t, hdev, nullptr)) != HB_OK) return rc;
+            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, (size_t) n, hdev, t, hdev + k, -1.0, nullptr)) != HB_OK) return rc;
+            HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T) * (size_t) (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            HB_CUDA(cudaStreamSynchronize(ctx->stream));
+            coeffs.assign(hhost, hhost + k);
+            const R nrm = (R) std::sqrt((double) hreal(hhost[k]));
+
+            for (int i = 0; i < inner; i++) h_rot(coeffs[i], coeffs[i + 1], C[i], S[i]);
+            T isin = zero_of<T>(), beta = from_real<T>(nrm);
+            R icos = 0;
+            h_rotg(coeffs[inner], beta, icos, isin);
+            H.insert(H.end(), coeffs.begin(), coeffs.end());
+            S.push_back(isin); C.push_back(icos);
+            inner_res = habs(hmul(S.back(), Z.back()));
+            inner++;
+            if ((inner_res > tol) && (inner < restart)){
+                if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev + k, W + (size_t) inner * n, nullptr)) != HB_OK) return rc;
+                Z.push_back(zero_of<T>());
+                h_rot(Z[inner - 1], Z[inner], C.back(), S.back());
+            }
+        }
+        if (!H.empty()){
+            const int nz = (int) Z.size();
+            h_tpsv_unn(nz, H, Z);
+            memcpy(hhost, Z.data(), sizeof(T) * (size_t) nz);
+            HB_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(T) * (size_t) nz, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, nz, W, (size_t) n, hdev, x, nullptr, 1.0, nullptr)) != HB_OK) return rc;
+            HB_CUDA(cudaStreamSynchronize(ctx->stream));      // hhost is reused by the next outer iteration
+        }
+        outer++;
+        outer_res = inner_res;
+    }
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iters) *iters = total;
+    if (res) *res = (double) outer_res;
+    return HB_OK;
+}
+
+}
+
+extern "C" {
+
+int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+    HB_ARG(ctx && A && b && x, "null");
+    HB_ARG(A->rows == A->cols, "CG needs a square matrix");
+    const int n = A->rows, dtype = A->dtype;
+    const size_t es = hb_dtype_size(dtype);
+    if (n == 0){ if (iters) *iters = 1; if (res) *res = 0; return HB_OK; }
+    dev_buffer work;
+    int rc;
+    // r | p | Ap | state
+    const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256;
+    if ((rc = work.alloc(3 * vec_bytes + 256)) != HB_OK) return rc;
+    char *base = (char*) work.p;
+    void *r = base, *p = base + vec_bytes, *Ap = base + 2 * vec_bytes, *state = base + 3 * vec_bytes;
+    void *pap = (char*) state + hb_cg_state_pap_offset(dtype);
+    const int *done_flag = reinterpret_cast<const int*>((char*) state + hb_cg_state_done_offset(dtype));
+    cg_host_status_h *hstat = reinterpret_cast<cg_host_status_h*>(reinterpret_cast<char*>(ctx->hscalars) + 256);
+    void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 256;
+    hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
+
+    if ((rc = hb_spmv_internal(ctx, A, x, Ap, nullptr)) != HB_OK) return rc;                                  // p = A x  (cg:110)
+    if ((rc = hb_cg_setup_internal(ctx, dtype, n, state, tol, max_iter, b, Ap, r, p, hstat_dev)) != HB_OK) return rc;
+
+    event_pair evs;
+    HB_CUDA(cudaEventCreateWithFlags(&evs.ev[0], cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&evs.ev[1], cudaEventDisableTiming));
+    const int batch = 8;
+    long long it = 0;
+    for (long long bidx = 0; ; bidx++){
+        for (int j = 0; j < batch; j++, it++){
+            const int parity = (int) (it & 1);
+            if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;               // Ap = A p ; <p,Ap>
+            if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, p, Ap, x, r, hstat_dev)) != HB_OK) return rc;
+            if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, r, p)) != HB_OK) return rc;
+        }
+        HB_CUDA(cudaEventRecord(evs.ev[bidx & 1], ctx->stream));
+        if (bidx > 0){
+            HB_CUDA(cudaEventSynchronize(evs.ev[(bidx - 1) & 1]));
+            if (hstat->done) break;
+        }
+    }
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iters) *iters = hstat->iterations;
+    if (res) *res = hstat->rnorm;
+    return HB_OK;
+}
+
+int hb_gmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, int *iters, double *res){
+    HB_ARG(ctx && A && b && x, "null");
+    HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
+    HB_ARG(restart >= 1, "restart must be positive");
+    if (A->rows == 0){ if (iters) *iters = 0; if (res) *res = 0; return HB_OK; }
+    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
+    return HB_OK;
+}
+
+}

@@ -1,0 +1,381 @@
+// hb_spmv.cu — CSR sparse matrix-vector product on sm_100a for float, double, complex<float/double>.
+// Replaces cusparseCreateCsr / cusparseSpMV_bufferSize / cusparseSpMV behind gpu_sparse_matrix
+// (reference gpu/hala_cuda_sparse_general.hpp:72-90, 245-277) and restates, per row, sparse_gemv_array
+// (sparse/hala_sparse_utils.hpp:103-118).
+//
+// op 'N', two kernel families (chosen per matrix by a one-time analysis, hb_csr_create):
+//   * staged tiles ("thread per row", with warp-cooperative handling of long row segments):
+//       a CTA owns ROWS consecutive rows; their CSR slice [pntr[r0], pntr[r0+ROWS)) is contiguous in memory and is
+//       streamed into shared memory in chunks of CH non-zeros with 128-bit, perfectly coalesced, evict-first loads
+//       of col_idx and values; then thread t walks row r0+t inside shared memory, left to right (the reference's
+//       summation order), gathering x through L1/L2.  Adjacent lanes own adjacent rows, so for banded/stencil
+//       matrices the gather of step k is x[c_k + lane]: one or two 128-byte lines per warp instruction instead of
+//       one line per lane.  Row segments longer than LONGSEG inside a chunk are handed to whole warps
+//       (shuffle reduction) so that heavy-tailed row-length distributions do not serialise on one lane.
+//   * row-vector ("sub-warp / warp per row"): TPR lanes per row, strided walk, shuffle reduction; used for matrices
+//       whose mean row is long, and as the unaligned fallback.
+// Both fuse an optional <x, y> dot (conjugated) into the same pass for CG (hb_spmv_dot).
+// op 'T' / 'C': y = beta y, then atomic scatter y[col] += alpha x[row] op(val) (first cut).
+#include "hb_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ analysis
+__global__ void csr_analyse_kernel(int rows, const int *pntr, int *stats){
+    int mx = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x)
+        mx = max(mx, pntr[i + 1] - pntr[i]);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&stats[0], mx);
+}
+
+// ------------------------------------------------------------------------------------------------ staging helpers
+template<typename T> struct stage_cfg;      // CH = non-zeros per chunk
+template<> struct stage_cfg<float>        { static constexpr int CH = 4096; };
+template<> struct stage_cfg<double>       { static constexpr int CH = 4096; };
+template<> struct stage_cfg<cplx<float>>  { static constexpr int CH = 4096; };
+template<> struct stage_cfg<cplx<double>> { static constexpr int CH = 2048; };
+
+static constexpr int LONGSEG = 128;         // row segment (within one chunk) handed to a whole warp
+static constexpr int MAXLONG = 4096 / LONGSEG;
+
+__device__ __forceinline__ int4 ldcs_int4(const int *p){ return __ldcs(reinterpret_cast<const int4*>(p)); }
+
+// copy 4 consecutive values global -> shared with 128-bit transactions (both sides 16-byte aligned)
+template<typename T> __device__ __forceinline__ void stage4(const T *g, T *s);
+template<> __device__ __forceinline__ void stage4<float>(const float *g, float *s){
+    *reinterpret_cast<float4*>(s) = __ldcs(reinterpret_cast<const float4*>(g));
+}
+template<> __device__ __forceinline__ void stage4<double>(const double *g, double *s){
+    double2 a = __ldcs(reinterpret_cast<const double2*>(g)), b = __ldcs(reinterpret_cast<const double2*>(g) + 1);
+    reinterpret_cast<double2*>(s)[0] = a; reinterpret_cast<double2*>(s)[1] = b;
+}
+template<> __device__ __forceinline__ void stage4<cplx<float>>(const cplx<float> *g, cplx<float> *s){
+    float4 a = __ldcs(reinterpret_cast<const float4*>(g)), b = __ldcs(reinterpret_cast<const float4*>(g) + 1);
+    reinterpret_cast<float4*>(s)[0] = a; reinterpret_cast<float4*>(s)[1] = b;
+}
+template<> __device__ __forceinline__ void stage4<cplx<double>>(const cplx<double> *g, cplx<double> *s){
+    const double2 *gp = reinterpret_cast<const double2*>(g);
+    double2 a = __ldcs(gp), b = __ldcs(gp + 1), c = __ldcs(gp + 2), d = __ldcs(gp + 3);
+    double2 *sp = reinterpret_cast<double2*>(s);
+    sp[0] = a; sp[1] = b; sp[2] = c; sp[3] = d;
+}
+
+// ------------------------------------------------------------------------------------------------ staged tiles, op N
+// DOT: also accumulate conj(x[row]) * (A x)[row] and publish the grid-wide sum to *dot_out (alpha = 1, beta = 0 semantics).
+template<typename T, int ROWS, bool VEC, bool DOT>
+__global__ void __launch_bounds__(ROWS) spmv_tiles_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
+                                                          const T * __restrict__ vals, const T * __restrict__ x, T *y,
+                                                          scalar_arg<T> alpha_s, scalar_arg<T> beta_s,
+                                                          void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag){
+    constexpr int CH = stage_cfg<T>::CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T   *sv = reinterpret_cast<T*>(smem_raw);
+    int *sc = reinterpret_cast<int*>(smem_raw + sizeof(T) * CH);
+    __shared__ int   long_row[MAXLONG], long_lo[MAXLONG], long_hi[MAXLONG];
+    __shared__ int   long_count;
+    __shared__ T     red[32];
+    T *long_sum = reinterpret_cast<T*>(smem_raw + (sizeof(T) + sizeof(int)) * CH);   // MAXLONG entries
+
+    if (skip_flag && *skip_flag) return;
+
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntiles = (rows + ROWS - 1) / ROWS;
+    T dot_acc = zero_of<T>();
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        const int r0 = tile * ROWS, row = r0 + tid;
+        const int rend = min(r0 + ROWS, rows);
+        const int nz0 = __ldg(pntr + r0), nz1 = __ldg(pntr + rend);
+        int rs = nz1, re = nz1;
+        if (row < rows){ rs = __ldg(pntr + row); re = __ldg(pntr + row + 1); }
+        T sum = zero_of<T>();
+        const int abase = VEC ? (nz0 & ~3) : nz0;
+        for (int cb = abase; cb < nz1; cb += CH){
+            const int cend = min(cb + CH, nz1);
+            if (tid == 0) long_count = 0;
+            // ---- stage chunk [cb, cend) : coalesced, 128-bit when aligned
+            if (VEC){
+                const int nq = (cend - cb + 3) >> 2;
+                for (int q = tid; q < nq; q += ROWS){
+                    const int e = cb + 4 * q;
+                    if (e + 3 < nnz){
+                        *reinterpret_cast<int4*>(sc + 4 * q) = ldcs_int4(indx + e);
+                        stage4<T>(vals + e, sv + 4 * q);
+                    }else{
+                        for (int k = 0; k < 4; k++) if (e + k < nnz){ sc[4 * q + k] = indx[e + k]; sv[4 * q + k] = vals[e + k]; }
+                    }
+                }
+            }else{
+                for (int i = tid; i < cend - cb; i += ROWS){ sc[i] = __ldcs(indx + cb + i); sv[i] = ld_stream(vals + cb + i); }
+            }
+            __syncthreads();
+            // ---- consume: thread per row, left to right
+            const int lo = max(rs, cb) - cb, hi = min(re, cend) - cb;
+            if (hi - lo >= LONGSEG){
+                int slot = atomicAdd(&long_count, 1);
+                long_row[slot] = tid; long_lo[slot] = lo; long_hi[slot] = hi;
+            }else{
+                #pragma unroll 4
+                for (int j = lo; j < hi; j++) sum = hfma(sv[j], ld_ro(x + sc[j]), sum);
+            }
+            __syncthreads();
+            const int nlong = long_count;
+            if (nlong > 0){         // block-uniform
+                for (int s = warp; s < nlong; s += ROWS / 32){
+                    T part = zero_of<T>();
+                    for (int j = long_lo[s] + lane; j < long_hi[s]; j += 32) part = hfma(sv[j], ld_ro(x + sc[j]), part);
+                    part = warp_sum(part);
+                    if (lane == 0) long_sum[s] = part;
+                }
+                __syncthreads();
+                for (int s = 0; s < nlong; s++) if (long_row[s] == tid) sum = hadd(sum, long_sum[s]);
+                __syncthreads();
+            }
+        }
+        if (row < rows){
+            if (DOT){
+                y[row] = sum;
+                dot_acc = hfma(hconj(ld_ro(x + row)), sum, dot_acc);
+            }else{
+                T out = hmul(alpha, sum);
+                if (use_beta) out = hfma(beta, y[row], out);
+                y[row] = out;
+            }
+        }
+    }
+    if (DOT){
+        T *partials = reinterpret_cast<T*>(partials_v);
+        T b = block_sum(dot_acc, red);
+        if (tid == 0) partials[blockIdx.x] = b;
+        if (last_block_arrives(ticket)){
+            T total = sum_partials<T>(partials, gridDim.x, 1, red);
+            if (tid == 0) *dot_out = total;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ row-vector, op N
+template<typename T, int TPR, bool DOT>
+__global__ void __launch_bounds__(256) spmv_rowvec_kernel(int rows, const int * __restrict__ pntr, const int * __restrict__ indx,
+                                                          const T * __restrict__ vals, const T * __restrict__ x, T *y,
+                                                          scalar_arg<T> alpha_s, scalar_arg<T> beta_s,
+                                                          void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag){
+    __shared__ T red[32];
+    if (skip_flag && *skip_flag) return;
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    const int sub = threadIdx.x % TPR;
+    const long long group = (blockIdx.x * (long long) blockDim.x + threadIdx.x) / TPR;
+    const long long ngroups = (long long) gridDim.x * blockDim.x / TPR;
+    T dot_acc = zero_of<T>();
+    // every lane of a warp runs the same number of outer iterations (rows padded up) so the shuffles stay converged
+    const long long rows_pad = ((long long) rows + (32 / TPR) - 1) / (32 / TPR) * (32 / TPR);
+    for (long long row = group; row < rows_pad; row += ngroups){
+        T sum = zero_of<T>();
+        if (row < rows){
+            const int rs = __ldg(pntr + row), re = __ldg(pntr + row + 1);
+            for (int j = rs + sub; j < re; j += TPR) sum = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), sum);
+        }
+        #pragma unroll
+        for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
+        if (sub == 0 && row < rows){
+            if (DOT){
+                y[row] = sum;
+                dot_acc = hfma(hconj(ld_ro(x + row)), sum, dot_acc);
+            }else{
+                T out = hmul(alpha, sum);
+                if (use_beta) out = hfma(beta, y[row], out);
+                y[row] = out;
+            }
+        }
+    }
+    if (DOT){
+        T *partials = reinterpret_cast<T*>(partials_v);
+        T b = block_sum(dot_acc, red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = b;
+        if (last_block_arrives(ticket)){
+            T total = sum_partials<T>(partials, gridDim.x, 1, red);
+            if (threadIdx.x == 0) *dot_out = total;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ op T / C (scatter)
+template<typename T> __global__ void scale_or_zero_kernel(int n, scalar_arg<T> beta_s, T *y){
+    const T beta = get_scalar(beta_s);
+    const bool z = hiszero(beta);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        y[i] = z ? zero_of<T>() : hmul(beta, y[i]);
+}
+__device__ __forceinline__ void atomic_add(float *p, float v){ atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add(double *p, double v){ atomicAdd(p, v); }
+template<typename R> __device__ __forceinline__ void atomic_add(cplx<R> *p, cplx<R> v){
+    atomicAdd(&p->re, v.re); atomicAdd(&p->im, v.im);
+}
+template<typename T, int TPR, bool CONJ>
+__global__ void __launch_bounds__(256) spmv_trans_kernel(int rows, const int * __restrict__ pntr, const int * __restrict__ indx,
+                                                         const T * __restrict__ vals, const T * __restrict__ x, T *y, scalar_arg<T> alpha_s){
+    const T alpha = get_scalar(alpha_s);
+    const int sub = threadIdx.x % TPR;
+    const long long group = (blockIdx.x * (long long) blockDim.x + threadIdx.x) / TPR;
+    const long long ngroups = (long long) gridDim.x * blockDim.x / TPR;
+    for (long long row = group; row < rows; row += ngroups){
+        const int rs = __ldg(pntr + row), re = __ldg(pntr + row + 1);
+        const T ax = hmul(alpha, ld_ro(x + row));
+        for (int j = rs + sub; j < re; j += TPR){
+            T v = ld_stream(vals + j);
+            atomic_add(y + __ldcs(indx + j), hmul(ax, CONJ ? hconj(v) : v));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline bool aligned16p(const void *p){ return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template<typename T, int ROWS, bool DOT>
+static int launch_tiles(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    constexpr int CH = stage_cfg<T>::CH;
+    const size_t smem = (sizeof(T) + sizeof(int)) * CH + sizeof(T) * MAXLONG;
+    const int ntiles = (A->rows + ROWS - 1) / ROWS;
+    const int per_sm = (int) std::min<size_t>(2048 / ROWS, (220 * 1024) / (smem + 1024));
+    int grid = std::min(ntiles, ctx->num_sms * per_sm);
+    if (grid < 1) grid = 1;
+    if (A->vec_aligned){
+        static bool attr_set = false;
+        auto k = spmv_tiles_kernel<T, ROWS, true, DOT>;
+        if (!attr_set){ HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_set = true; }
+        k<<<grid, ROWS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
+                                             ctx->partials, ctx->tickets + 1, dot_out, skip);
+    }else{
+        static bool attr_set = false;
+        auto k = spmv_tiles_kernel<T, ROWS, false, DOT>;
+        if (!attr_set){ HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_set = true; }
+        k<<<grid, ROWS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
+                                             ctx->partials, ctx->tickets + 1, dot_out, skip);
+    }
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+
+template<typename T, int TPR, bool DOT>
+static int launch_rowvec(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    const long long threads = (long long) A->rows * TPR;
+    int grid = (int) std::min<long long>((threads + 255) / 256, (long long) ctx->num_sms * 8);
+    if (grid < 1) grid = 1;
+    spmv_rowvec_kernel<T, TPR, DOT><<<grid, 256, 0, ctx->stream>>>(A->rows, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
+                                                                   ctx->partials, ctx->tickets + 1, dot_out, skip);
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+
+// variant: 0 auto, 1 row-vector, 2 staged tiles
+template<typename T, bool DOT>
+int hb_spmv_n_typed(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    int variant = A->variant;
+    const double mean = A->mean_row_nnz;
+    if (variant == 0 || variant == 3) variant = (mean > 96.0) ? 1 : 2;
+    if (variant == 2){
+        if (mean >= 16.0) return launch_tiles<T, 128, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        return launch_tiles<T, 256, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    }
+    if (mean > 48.0)      return launch_rowvec<T, 32, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    else if (mean > 20.0) return launch_rowvec<T, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    else if (mean > 6.0)  return launch_rowvec<T, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    return launch_rowvec<T, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+}
+
+// used by hb_solvers.cu (fused CG): y = A x, *dot_dev = <x,y>, skipped entirely when *skip != 0
+int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip){
+    HB_DISPATCH(A->dtype, {
+        scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
+        scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
+        return hb_spmv_n_typed<T, true>(ctx, A, (const T*) x, (T*) y, one, zero, (T*) dot_dev, skip);
+    });
+    return HB_OK;
+}
+int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip){
+    HB_DISPATCH(A->dtype, {
+        scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
+        scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
+        return hb_spmv_n_typed<T, false>(ctx, A, (const T*) x, (T*) y, one, zero, nullptr, skip);
+    });
+    return HB_OK;
+}
+
+extern "C" {
+
+int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int *pntr, const int *indx, const void *vals, hb_csr **out){
+    HB_ARG(ctx && out, "null");
+    HB_ARG(dtype >= HB_F32 && dtype <= HB_C64, "dtype");
+    HB_ARG(rows >= 0 && cols >= 0 && nnz >= 0, "negative dimension");
+    HB_ARG(rows == 0 || pntr, "pntr is null");
+    HB_ARG(nnz == 0 || (indx && vals), "indx/vals null");
+    hb_csr *A = new hb_csr();
+    A->ctx = ctx; A->dtype = dtype; A->rows = rows; A->cols = cols; A->nnz = nnz;
+    A->pntr = pntr; A->indx = indx; A->vals = vals;
+    A->vec_aligned = aligned16p(indx) && aligned16p(vals);
+    A->mean_row_nnz = rows > 0 ? (double) nnz / rows : 0.0;
+    // one-time analysis: longest row (decides nothing structural today beyond reporting, but costs one tiny kernel)
+    A->stats_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048);
+    HB_CUDA(cudaMemsetAsync(A->stats_dev, 0, sizeof(int), ctx->stream));
+    if (rows > 0){
+        int grid = hb_grid_for(ctx, (size_t) rows, 256, 8);
+        csr_analyse_kernel<<<grid, 256, 0, ctx->stream>>>(rows, pntr, A->stats_dev);
+        HB_LAUNCH_CHECK(ctx);
+    }
+    HB_CUDA(cudaMemcpyAsync(&A->max_row_nnz, A->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = A;
+    return HB_OK;
+}
+
+int hb_csr_destroy(hb_csr *csr){ delete csr; return HB_OK; }
+
+int hb_csr_info(const hb_csr *A, int *dtype, int *rows, int *cols, int *nnz, int *max_row_nnz){
+    HB_ARG(A, "csr is null");
+    if (dtype) *dtype = A->dtype;
+    if (rows) *rows = A->rows;
+    if (cols) *cols = A->cols;
+    if (nnz) *nnz = A->nnz;
+    if (max_row_nnz) *max_row_nnz = A->max_row_nnz;
+    return HB_OK;
+}
+
+int hb_csr_set_variant(hb_csr *A, int variant){ HB_ARG(A && variant >= 0 && variant <= 3, "variant"); A->variant = variant; return HB_OK; }
+
+int hb_spmv_buffer_size(const hb_csr *A, char trans, size_t *bytes){ (void) trans; HB_ARG(A && bytes, "null"); *bytes = 0; return HB_OK; }
+
+int hb_spmv(hb_ctx *ctx, const hb_csr *A, char trans, const void *alpha, const void *x, const void *beta, void *y){
+    HB_ARG(ctx && A && alpha && beta, "null");
+    const int ny = hb_is_n(trans) ? A->rows : A->cols;
+    if (ny == 0) return HB_OK;
+    HB_ARG(y, "y is null");
+    HB_ARG(x || (hb_is_n(trans) ? A->cols : A->rows) == 0, "x is null");
+    HB_DISPATCH(A->dtype, {
+        scalar_arg<T> a = make_scalar<T>(ctx, alpha), b = make_scalar<T>(ctx, beta);
+        if (hb_is_n(trans)) return hb_spmv_n_typed<T, false>(ctx, A, (const T*) x, (T*) y, a, b, nullptr, nullptr);
+        int grid = hb_grid_for(ctx, (size_t) ny, 256, 8);
+        scale_or_zero_kernel<T><<<grid, 256, 0, ctx->stream>>>(ny, b, (T*) y);
+        HB_LAUNCH_CHECK(ctx);
+        if (A->rows > 0 && A->nnz > 0){
+            const bool cj = hb_is_c(trans) && is_cplx<T>::value;
+            const long long threads = (long long) A->rows * 4;
+            int g2 = (int) std::min<long long>((threads + 255) / 256, (long long) ctx->num_sms * 8);
+            if (cj) spmv_trans_kernel<T, 4, true><<<g2, 256, 0, ctx->stream>>>(A->rows, A->pntr, A->indx, (const T*) A->vals, (const T*) x, (T*) y, a);
+            else    spmv_trans_kernel<T, 4, false><<<g2, 256, 0, ctx->stream>>>(A->rows, A->pntr, A->indx, (const T*) A->vals, (const T*) x, (T*) y, a);
+            HB_LAUNCH_CHECK(ctx);
+        }
+    });
+    return HB_OK;
+}
+
+int hb_spmv_dot(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev){
+    HB_ARG(ctx && A && dot_dev, "null");
+    HB_ARG(A->rows == A->cols, "hb_spmv_dot needs a square matrix");
+    if (A->rows == 0){ HB_CUDA(cudaMemsetAsync(dot_dev, 0, hb_dtype_size(A->dtype), ctx->stream)); return HB_OK; }
+    return hb_spmv_dot_internal(ctx, A, x, y, dot_dev, nullptr);
+}
+
+}

@@ -1,0 +1,125 @@
+/* halab200.h — C ABI of libhalab200.so, the B200-native (sm_100a) backend for LIBHALA/hala's sparse
+ * iterative-solve hot path.  This is the drop-in boundary: the replacement `gpu/` header layer
+ * (the .hpp files under hala_b200/gpu/, source-compatible with the reference's L4 headers) calls ONLY these entry points;
+ * anything that can bind a C function (ctypes, cgo, JNI, ...) can call them too.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int status (HB_OK == 0); hb_last_error() gives the message of the last
+ *     failure on the calling thread.  The C++ header layer turns a non-zero status into std::runtime_error,
+ *     as the reference does for CUDA/cuBLAS/cuSPARSE statuses (gpu/hala_cuda_common.hpp:78-152).
+ *   - dtype: HB_F32/HB_F64/HB_C32/HB_C64 == float/double/complex<float>/complex<double>
+ *     (the reference's cuda_call_backend 4-way dispatch, gpu/hala_cuda_common.hpp:159-184).
+ *   - all array arguments are DEVICE pointers on the context's device unless the name says host.
+ *   - scalars (alpha, beta, results) are passed by pointer to a value of `dtype` (results of nrm2: its real
+ *     type).  In HB_POINTER_HOST mode (default) they are host pointers and scalar-returning calls are
+ *     host-synchronous, exactly like the reference (gpu/hala_gpu_blas1.hpp:186-197); in HB_POINTER_DEVICE
+ *     mode they are device pointers and nothing synchronises (reference: gpu_pntr<device_pntr>,
+ *     gpu/hala_gpu_engine.hpp:410-446).
+ *   - a context is NOT thread-safe (one engine per host thread per device — the reference's contract).
+ *   - kernels are launched on the context's stream (default: the legacy default stream, as the reference).
+ *   - 32-bit CSR indices, 0-based (reference: CUSPARSE_INDEX_32I / BASE_ZERO, gpu/hala_cuda_sparse_general.hpp:85-87);
+ *     vector lengths are int like BLAS, but every internal offset is 64-bit (rows*restart > 2^31 is legal).
+ */
+#ifndef HALAB200_H
+#define HALAB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_ctx hb_ctx;   /* replaces the cuBLAS+cuSPARSE handle pair held by gpu_engine (gpu/hala_gpu_engine.hpp:47-163) */
+typedef struct hb_csr hb_csr;   /* replaces cusparseSpMatDescr_t + cached buffer sizes of gpu_sparse_matrix (gpu/hala_cuda_sparse_general.hpp:191-375) */
+
+enum { HB_F32 = 0, HB_F64 = 1, HB_C32 = 2, HB_C64 = 3 };
+enum { HB_OK = 0, HB_ERR_CUDA = 1, HB_ERR_ARG = 2, HB_ERR_ALLOC = 3, HB_ERR_UNSUPPORTED = 4, HB_ERR_NCCL = 5, HB_ERR_NOT_CONVERGED = 6 };
+enum { HB_POINTER_HOST = 0, HB_POINTER_DEVICE = 1 };
+enum { HB_H2D = 0, HB_D2H = 1, HB_D2D = 2 };
+
+/* ---- library / context: gpu_engine (gpu/hala_gpu_engine.hpp:60-117), gpu_device_count (gpu/hala_cuda_common.hpp:195) ---- */
+const char* hb_version(void);
+const char* hb_last_error(void);
+int hb_device_count(int *count);
+int hb_ctx_create(int device, hb_ctx **ctx);
+int hb_ctx_destroy(hb_ctx *ctx);
+int hb_ctx_device(const hb_ctx *ctx, int *device);
+int hb_ctx_set_stream(hb_ctx *ctx, void *cuda_stream);          /* gpu_engine::set_stream  (:86) */
+int hb_ctx_get_stream(const hb_ctx *ctx, void **cuda_stream);
+int hb_ctx_sync(hb_ctx *ctx);                                   /* gpu_engine::synchronize (:83) */
+int hb_ctx_set_pointer_mode(hb_ctx *ctx, int mode);             /* set/reset_blas_device_pntr (:105-111) */
+int hb_ctx_get_pointer_mode(const hb_ctx *ctx, int *mode);      /* get_blas_pointer_mode (:112-117) */
+int hb_ctx_launch_count(const hb_ctx *ctx, long long *count);   /* kernels launched through this context so far */
+
+/* ---- device timers (CUDA events on the context stream) — measurement plumbing for bench.py; the reference only has the
+ *      wall-clock hala::chronometer (common/hala_core.hpp:155-162) ---- */
+int hb_timer_start(hb_ctx *ctx);                                /* records the start event on the context stream */
+int hb_timer_stop(hb_ctx *ctx, float *milliseconds);            /* records stop, synchronises on it, returns elapsed */
+
+/* ---- memory: gpu_allocate / gpu_free / gpu_copy_n (gpu/hala_cuda_common.hpp:253-330), gpu_vector::fill (gpu/hala_gpu_vector.hpp:147),
+ *      set_zero (gpu/hala_gpu_engine.hpp:335-352) ---- */
+int hb_malloc(hb_ctx *ctx, size_t bytes, void **ptr);
+int hb_free(hb_ctx *ctx, void *ptr);
+int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);        /* host-synchronous */
+int hb_memcpy_async(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);  /* on the context stream */
+int hb_memset_zero(hb_ctx *ctx, void *ptr, size_t bytes);
+int hb_fill(hb_ctx *ctx, int dtype, size_t n, const void *host_value, void *x);        /* dtype may also be -1: int32 */
+int hb_host_alloc(size_t bytes, void **ptr);                                           /* pinned host memory */
+int hb_host_free(void *ptr);
+
+/* ---- CSR matrix view: gpu_sparse_matrix ctor / make_sparse_matrix (gpu/hala_cuda_sparse_general.hpp:215-227,382-401) ----
+ * Non-owning of pntr/indx/vals (as the reference, :186-190,370-371); owns its one-time analysis tables. */
+int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz,
+                  const int *pntr, const int *indx, const void *vals, hb_csr **csr);
+int hb_csr_destroy(hb_csr *csr);
+int hb_csr_info(const hb_csr *csr, int *dtype, int *rows, int *cols, int *nnz, int *max_row_nnz);
+/* workspace bytes a caller must supply to hb_spmv: always 0 here (reference: cusparseSpMV_bufferSize, :245-262,342-351) */
+int hb_spmv_buffer_size(const hb_csr *csr, char trans, size_t *bytes);
+/* y = alpha op(A) x + beta y; y is NOT read when beta == 0 (host mode) — gpu_sparse_matrix::gemv (:264-277) -> cusparseSpMV */
+int hb_spmv(hb_ctx *ctx, const hb_csr *csr, char trans, const void *alpha, const void *x, const void *beta, void *y);
+/* fused: y = A x and *dot_dev = <x, y> (conjugated for complex) in one pass; result stays on the device.
+ * Replaces cusparseSpMV + cublas?dot of the CG loop (hex/solvers/hala_solvers_cg.hpp:129-133). */
+int hb_spmv_dot(hb_ctx *ctx, const hb_csr *csr, const void *x, void *y, void *dot_dev);
+/* selects the SpMV kernel variant for op 'N': 0 = auto, 1 = row-vector (sub-warp per row), 2 = staged tiles (LDG),
+ * 3 = staged tiles (TMA bulk copy pipeline).  For benchmarking; auto is what the header layer uses. */
+int hb_csr_set_variant(hb_csr *csr, int variant);
+
+/* ---- BLAS-1: gpu/hala_gpu_blas1.hpp  vcopy :48-65, norm2 :102-121, dot<conj> :178-198, axpy :204-222, scal :228-245 ---- */
+int hb_copy(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *y, int incy);
+int hb_axpy(hb_ctx *ctx, int dtype, int n, const void *alpha, const void *x, int incx, void *y, int incy);
+int hb_scal(hb_ctx *ctx, int dtype, int n, const void *alpha, void *x, int incx);
+int hb_dot (hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, const void *y, int incy, void *result);
+int hb_nrm2(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result);
+
+/* ---- BLAS-2 gemv, the Gram-Schmidt pair of GMRES: gpu/hala_gpu_blas2.hpp:39-62 (cublas?gemv), column-major A ---- */
+int hb_gemv(hb_ctx *ctx, int dtype, char trans, int M, int N, const void *alpha, const void *A, int lda,
+            const void *x, int incx, const void *beta, void *y, int incy);
+
+/* ---- fused Krylov building blocks (device-resident scalars; no host synchronisation) ----
+ * hb_multi_dot : h[c] = sum_i op(W[i,c]) r[i], c < k, one pass over r and the k basis columns (conj != 0 -> op = conj)
+ * hb_multi_axpy_nrm2 : r -= W h (h on device), *nrm2sq_dev = sum |r_i|^2 of the UPDATED r, same pass
+ *   together they replace gemv('T')+gemv('N')+nrm2 of krylov_project (hex/solvers/hala_solvers_gmres.hpp:67-72,192)
+ * hb_axpy2_nrm2 : x += a p ; r -= a q ; *rr_dev = <r,r>   (CG update, hala_solvers_cg.hpp:135-138) with a read from device
+ * hb_xpby : p = r + b p (b on device)                     (hala_solvers_cg.hpp:147-148)                              */
+int hb_multi_dot(hb_ctx *ctx, int dtype, int conj, int rows, int k, const void *W, size_t ldw, const void *r, void *h_dev);
+int hb_multi_axpy_nrm2(hb_ctx *ctx, int dtype, int rows, int k, const void *W, size_t ldw, const void *h_dev,
+                       void *r, void *nrm2sq_dev);
+int hb_axpy2_nrm2(hb_ctx *ctx, int dtype, int n, const void *a_dev, const void *p, const void *q, void *x, void *r, void *rr_dev);
+int hb_xpby(hb_ctx *ctx, int dtype, int n, const void *r, const void *b_dev, void *p);
+
+/* ---- solvers with the iteration on the device ----
+ * hb_cg : unpreconditioned CG, recurrence, iteration counter and stop test of solve_cg_core
+ *   (hex/solvers/hala_solvers_cg.hpp:92-156; stop: iterations == max_iter || ||r||_2 < tol, :225), three fused kernels per
+ *   iteration, scalars never leave the device; the host only polls a completion flag.
+ *   x: initial guess in, solution out. *iters = operator applications (reference return value), *res = final ||r||_2.
+ * hb_gmres : restarted GMRES(m), identity preconditioner, classical Gram-Schmidt as fused multi-dot/multi-axpy,
+ *   Givens/Hessenberg on the host exactly as hala_solvers_gmres.hpp:127-230 (quirks included); cproj != 0 uses the
+ *   conjugated projection ('C'), which is what complex data needs (reference defect at :48,:69). */
+int hb_cg(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, int *iters, double *res);
+int hb_gmres(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_outer, int restart, int cproj,
+             int *iters, double *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

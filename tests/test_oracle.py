@@ -1,0 +1,186 @@
+"""CPU tests of the oracle itself (no GPU): the C restatement (oracle/hb_oracle.c) against
+  (1) vectors the reference's own tests hold (tests/golden/ref_tests.json, file:line inside),
+  (2) outputs of the unmodified reference recorded in tests/golden/ref_outputs.npz,
+  (3) known-answer iteration counts of the reference,
+  (4) the reference itself, live, when oracle/_ref was built in this container."""
+import numpy as np
+import pytest
+
+from hala_b200 import matgen as mg
+from helpers import DT, NP, SPMV_TOL, RED_TOL, assert_entrywise, assert_reduction, dense_from_csr, spmv_scale
+
+
+def _fixture(ref_tests, name, dt):
+    f = ref_tests[name]
+    return (np.array(f["pntr"], dtype=np.int32), np.array(f["indx"], dtype=np.int32), np.array(f["vals"], dtype=NP[dt]), f)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_reference_test_sparse_gemv(orc, ref_tests, dt):
+    """tests/sparse_tests.hpp:166-191: 5x5 tridiagonal, alpha = 2, beta = 0, ops N/T/C against the dense product."""
+    p, i, v, f = _fixture(ref_tests, "tridiag5", dt)
+    x = (np.array(f["x_real"], dtype=NP[dt]) if dt in ("f32", "f64")
+         else np.array([complex(a, b) for a, b in f["x_complex"]], dtype=NP[dt]))
+    A = dense_from_csr(p, i, v, 5)
+    for tr, op in (("N", A), ("T", A.T), ("C", A.conj().T)):
+        y = orc.spmv(p, i, v, x, alpha=2.0, beta=0.0, trans=tr)
+        np.testing.assert_allclose(y, 2.0 * (op @ x), rtol=1e-5 if "32" in dt else 1e-14)
+
+
+def test_reference_post_install_smoke(orc, ref_tests):
+    """cmake/post_install_test.sh:24-38: exact {4, 10, 18}."""
+    f = ref_tests["post_install"]
+    y = orc.spmv(np.array(f["pntr"], dtype=np.int32), np.array(f["indx"], dtype=np.int32), np.array(f["vals"]), np.array(f["x"]))
+    assert y.tolist() == f["y"]
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_reference_rect_matrix(orc, ref_tests, dt):
+    """tests/sparse_tests.hpp:140-152 fixture (5x6), as gemv N and T/C."""
+    p, i, v, f = _fixture(ref_tests, "rect5x6", dt)
+    A = dense_from_csr(p, i, v, 6)
+    x6, x5 = mg.probe_x(6, dt), mg.probe_x(5, dt)
+    rt = 1e-5 if "32" in dt else 1e-14
+    np.testing.assert_allclose(orc.spmv(p, i, v, x6, trans="N", ncols=6), A @ x6, rtol=rt, atol=rt)
+    np.testing.assert_allclose(orc.spmv(p, i, v, x5, trans="T", ncols=6), A.T @ x5, rtol=rt, atol=rt)
+    np.testing.assert_allclose(orc.spmv(p, i, v, x5, trans="C", ncols=6), A.conj().T @ x5, rtol=rt, atol=rt)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_reference_solver_fixtures(orc, ref_tests, dt):
+    """tests/solvers_tests.hpp matrices and xref = {1..5} (the reference solves them with ILU; here identity
+    preconditioner, same tolerance, same expected solution)."""
+    tol = 1e-4 if "32" in dt else 1e-9
+    xtol = 2e-3 if "32" in dt else 1e-7
+    for name in ("tridiag5", "cyclic5_spd"):
+        p, i, v, f = _fixture(ref_tests, name, dt)
+        xref = np.array(f["xref"], dtype=NP[dt])
+        b = dense_from_csr(p, i, v, 5) @ xref
+        x, it = orc.cg(p, i, v, b, tol, x0=f.get("x0"))
+        assert it <= 8
+        np.testing.assert_allclose(x, xref, atol=xtol)
+    p, i, v, f = _fixture(ref_tests, "nonsym5", dt)
+    xref = np.array(f["xref"], dtype=NP[dt])
+    b = dense_from_csr(p, i, v, 5) @ xref
+    x, it = orc.gmres(p, i, v, b, tol, f["restart"])
+    np.testing.assert_allclose(x, xref, atol=xtol)
+
+
+def test_known_answer_iteration_counts(orc, ref_tests):
+    """Iteration counts of the unmodified reference — exact for the serial restatement."""
+    ka = ref_tests["known_answers"]
+    for key in ("lap2d:256", "lap3d7:64", "lap3d27:64"):
+        name, n = key.split(":")
+        p, i, v = mg.GENERATORS[name](int(n))
+        _, it = orc.cg(p, i, v, mg.rhs(p.size - 1), 1e-8)
+        assert abs(it - ka["cg_iterations"][key]) <= 2, (key, it)
+    for key in ("convdiff7:24", "convdiff7:48"):
+        name, n = key.split(":")
+        p, i, v = mg.GENERATORS[name](int(n))
+        _, it = orc.gmres(p, i, v, mg.rhs(p.size - 1), 1e-8, 50)
+        assert abs(it - ka["gmres50_iterations"][key]) <= 2, (key, it)
+    p, i, v = mg.lap2d(1024)
+    b = mg.rhs(1024 * 1024)
+    y = orc.spmv(p, i, v, b)
+    assert y[0] == ka["spmv_spot_lap2d_1024_x_eq_b"]["y0"] and y[512 * 1024] == ka["spmv_spot_lap2d_1024_x_eq_b"]["y_half"]
+
+
+def test_oracle_matches_recorded_reference_spmv(orc, golden):
+    keys = [k for k in golden.files if k.startswith("spmv/")]
+    assert len(keys) >= 40
+    for k in keys:
+        _, mat, dt, tr = k.split("/")
+        name, n = mat.split(":")
+        if name == "powerlaw":
+            p, i, v = mg.powerlaw(N=int(n), lmax=700 if dt == "f64" else 500, dtype=dt)
+            x = mg.probe_x(int(n), dt)
+            y = orc.spmv(p, i, v, x)
+            scale = spmv_scale(p, i, v, x)
+        else:
+            p, i, v = mg.GENERATORS[name](int(n), dtype=dt)
+            N = p.size - 1
+            x, y0 = mg.probe_x(N, dt), mg.probe_x(N, dt, seed=99)
+            y = orc.spmv(p, i, v, x, alpha=2.0, beta=0.5, y=y0, trans=tr)
+            scale = spmv_scale(p, i, v, x, tr, alpha=2.0, beta=0.5, y0=y0)
+        assert_entrywise(y, golden[k], scale, SPMV_TOL[dt], k)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_oracle_matches_recorded_reference_blas(orc, golden, dt):
+    n = 1003
+    x, y = mg.probe_x(n * 3, dt, seed=3), mg.probe_x(n * 3, dt, seed=4)
+    a = 1.5 if dt in ("f32", "f64") else 1.5 - 0.5j
+    rt = 1e-5 if "32" in dt else 1e-13
+    for incx, incy in ((1, 1), (2, 3)):
+        tag = f"{dt}/{incx}{incy}"
+        np.testing.assert_allclose(orc.blas1("axpy", x, y, alpha=a, n=n, incx=incx, incy=incy), golden[f"axpy/{tag}"], rtol=rt, atol=rt)
+        np.testing.assert_array_equal(orc.blas1("copy", x, y, n=n, incx=incx, incy=incy), golden[f"copy/{tag}"])
+        np.testing.assert_allclose(orc.blas1("scal", x, alpha=a, n=n, incx=incx), golden[f"scal/{tag}"], rtol=rt, atol=rt)
+        xs, ys = x[::incx][:n], y[::incy][:n]
+        assert_reduction(orc.blas1("dot", x, y, n=n, incx=incx, incy=incy), golden[f"dot/{tag}"][0], xs, ys, dt, "dot")
+        assert_reduction(orc.blas1("dotu", x, y, n=n, incx=incx, incy=incy), golden[f"dotu/{tag}"][0], xs, ys, dt, "dotu")
+        np.testing.assert_allclose(orc.blas1("nrm2", x, n=n, incx=incx), golden[f"nrm2/{tag}"][0], rtol=RED_TOL[dt])
+    M, K = 777, 7
+    A = mg.probe_x(M * K, dt, seed=21)
+    xm, xk = mg.probe_x(M, dt, seed=22), mg.probe_x(K, dt, seed=23)
+    gt = 5e-4 if "32" in dt else 1e-12
+    np.testing.assert_allclose(orc.gemv("T", M, K, A, xm), golden[f"gemv/{dt}/T"], rtol=gt, atol=gt)
+    np.testing.assert_allclose(orc.gemv("C", M, K, A, xm), golden[f"gemv/{dt}/C"], rtol=gt, atol=gt)
+    np.testing.assert_allclose(orc.gemv("N", M, K, A, xk, alpha=-1.0, beta=1.0, y=xm), golden[f"gemv/{dt}/N"], rtol=gt, atol=gt)
+
+
+def test_oracle_matches_recorded_reference_solvers(orc, golden):
+    for k in [k for k in golden.files if k.startswith("cg/") and k.endswith("/iters")]:
+        _, mat, dt, _ = k.split("/")
+        name, n = mat.split(":")
+        p, i, v = mg.GENERATORS[name](int(n), dtype=dt)
+        tol = 1e-4 if "32" in dt else 1e-8
+        x, it = orc.cg(p, i, v, mg.rhs(p.size - 1, dt), tol)
+        assert abs(it - int(golden[k][0])) <= 2, (k, it, golden[k][0])
+        np.testing.assert_allclose(x, golden[k.replace("/iters", "/x")], atol=(50 * tol))
+    for k in [k for k in golden.files if k.startswith("gmres/") and k.endswith("/iters")]:
+        _, mat, dt, m, _ = k.split("/")
+        name, n = mat.split(":")
+        p, i, v = mg.GENERATORS[name](int(n), dtype=dt)
+        tol = 1e-4 if "32" in dt else 1e-8
+        x, it = orc.gmres(p, i, v, mg.rhs(p.size - 1, dt), tol, int(m[1:]), cproj=1 if dt.startswith("c") else 0)
+        assert abs(it - int(golden[k][0])) <= 2, (k, it, golden[k][0])
+        np.testing.assert_allclose(x, golden[k.replace("/iters", "/x")], atol=(50 * tol))
+
+
+def test_oracle_against_live_reference(orc):
+    """Only where oracle/_ref exists (built from /root/reference in the build container; shipped to the GPU box)."""
+    from oracle import binding
+    ref = binding.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    for dt in DT:
+        p, i, v = mg.lap3d27(7, dtype=dt)
+        x = mg.probe_x(p.size - 1, dt)
+        assert_entrywise(orc.spmv(p, i, v, x), ref.spmv(p, i, v, x), spmv_scale(p, i, v, x), SPMV_TOL[dt], dt)
+    p, i, v = mg.lap2d(96)
+    b = mg.rhs(96 * 96)
+    assert abs(orc.cg(p, i, v, b, 1e-8)[1] - ref.cg(p, i, v, b, 1e-8)[1]) <= 2
+    p, i, v = mg.convdiff7(14)
+    b = mg.rhs(14 ** 3)
+    assert abs(orc.gmres(p, i, v, b, 1e-8, 20)[1] - ref.gmres(p, i, v, b, 1e-8, 20)[1]) <= 2
+
+
+def test_generators_are_well_formed():
+    for name, n in (("lap2d", 17), ("lap3d7", 6), ("lap3d27", 5), ("convdiff7", 5), ("helmholtz7", 4)):
+        p, i, v = mg.GENERATORS[name](n)
+        N = mg.grid_rows(name, n)
+        assert p.size == N + 1 and p[0] == 0 and p[-1] == i.size == v.size
+        for r in range(N):
+            cols = i[p[r]:p[r + 1]]
+            assert np.all(np.diff(cols) > 0) and r in cols
+    assert mg.lap2d(1024)[1].size == 5 * 1024 * 1024 - 4 * 1024
+    assert mg.lap3d27(16)[1].size == (3 * 16 - 2) ** 3
+    p, i, v = mg.powerlaw(N=5000, lmax=900)
+    lens = np.diff(p)
+    assert lens.min() >= 1 and lens.max() <= 900 and lens.max() > 100
+    for r in (0, 17, 4999):
+        cols = i[p[r]:p[r + 1]]
+        assert np.all(np.diff(cols) > 0) and r in cols
+    A = dense_from_csr(*mg.powerlaw(N=300, lmax=64), 300)
+    assert np.all(np.abs(np.diag(A)) > np.sum(np.abs(A), axis=1) - np.abs(np.diag(A)))
