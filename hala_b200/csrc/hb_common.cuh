@@ -41,6 +41,10 @@ struct hb_csr {
     double mean_row_nnz = 0;
     int vec_aligned = 0;                // indx/vals 16-byte aligned -> 128-bit staging loads
     int *stats_dev = nullptr;           // [0] = max row length (analysis kernel)
+    // equal-nnz row partition for the persistent streaming kernel (hb_spmv_pipe.cuh): one table per pipeline config
+    int *cta_rows[2] = {nullptr, nullptr};
+    int  pipe_grid[2] = {0, 0};
+    int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
 };
 
 void hb_set_error(const std::string &msg);

@@ -301,7 +301,7 @@ int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int 
 // r += scale * W h  (scale = -1 for the projection, +1 for krylov_combine); optional |r|^2 of the result
 int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const void *W, size_t ldw, const void *h_dev, void *r,
                            void *nrm2sq_dev, double scale, const int *skip){
-    for (int c0 = 0; c0 < k; c0 += MD_KMAX){
+    for (int c0 = 0; c0 < k || c0 == 0; c0 += MD_KMAX){     // k == 0 still launches once: it delivers the norm
         const int kk = (k - c0 < MD_KMAX) ? (k - c0) : MD_KMAX;
         const bool last = (c0 + kk >= k);
         int grid = kr_grid(ctx, rows, KR_THREADS * 2);

@@ -17,6 +17,9 @@
 // Both fuse an optional <x, y> dot (conjugated) into the same pass for CG (hb_spmv_dot).
 // op 'T' / 'C': y = beta y, then atomic scatter y[col] += alpha x[row] op(val) (first cut).
 #include "hb_common.cuh"
+#include "hb_spmv_pipe.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------ analysis
 __global__ void csr_analyse_kernel(int rows, const int *pntr, int *stats){
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(ROWS) spmv_tiles_kernel(int rows, int nnz, con
 }
 
 // ------------------------------------------------------------------------------------------------ row-vector, op N
+static constexpr int RV_UNR = 4;
 template<typename T, int TPR, bool DOT>
 __global__ void __launch_bounds__(256) spmv_rowvec_kernel(int rows, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                           const T * __restrict__ vals, const T * __restrict__ x, T *y,
@@ -176,7 +180,21 @@ __global__ void __launch_bounds__(256) spmv_rowvec_kernel(int rows, const int * 
         T sum = zero_of<T>();
         if (row < rows){
             const int rs = __ldg(pntr + row), re = __ldg(pntr + row + 1);
-            for (int j = rs + sub; j < re; j += TPR) sum = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), sum);
+            // RV_UNR entries per lane per step, all col_idx/value loads issued before the first gather, all gathers before
+            // the first FMA: a row of up to RV_UNR*TPR entries costs ONE memory round trip instead of one per entry.
+            for (int base = rs + sub; base < re; base += RV_UNR * TPR){
+                int c[RV_UNR]; T v[RV_UNR], xv[RV_UNR];
+                #pragma unroll
+                for (int u = 0; u < RV_UNR; u++){
+                    const int j = base + u * TPR;
+                    c[u] = (j < re) ? __ldcs(indx + j) : -1;
+                    v[u] = (j < re) ? ld_stream(vals + j) : zero_of<T>();
+                }
+                #pragma unroll
+                for (int u = 0; u < RV_UNR; u++) xv[u] = (c[u] >= 0) ? ld_ro(x + c[u]) : zero_of<T>();
+                #pragma unroll
+                for (int u = 0; u < RV_UNR; u++) sum = hfma(v[u], xv[u], sum);
+            }
         }
         #pragma unroll
         for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
@@ -270,19 +288,99 @@ static int launch_rowvec(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_
     return HB_OK;
 }
 
-// variant: 0 auto, 1 row-vector, 2 staged tiles
+// ---- streaming pipeline launcher. Two (THREADS, STAGES) configurations are instantiated (HB_PIPE_CFG picks one for probing).
+template<int CFG> struct pipe_cfg;
+template<> struct pipe_cfg<0> { static constexpr int THREADS = 128, STAGES = 3; };
+template<> struct pipe_cfg<1> { static constexpr int THREADS = 256, STAGES = 3; };
+static size_t pipe_smem_bytes(int threads, int tpr, int stages, size_t es){
+    const size_t cap = (size_t) threads * (es == 16 ? 4 : 8), rows = threads / tpr;
+    return stages * ((cap + 4) * (es + sizeof(int)) + (rows + 4) * sizeof(int));
+}
+// lanes per row: the smallest power of two that keeps a typical row within ~7 entries per lane (<= two batches of four)
+static int pipe_tpr(double mean, size_t es){
+    const double slots = es == 16 ? 4.0 : 8.0;
+    return mean > 7.5 * slots ? 16 : mean > 3.75 * slots ? 8 : mean > 1.9 * slots ? 4 : mean > 0.94 * slots ? 2 : 1;
+}
+static int pipe_ctas_per_sm(int cfg, double mean, int dtype){
+    const int threads = cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS, stages = cfg == 0 ? pipe_cfg<0>::STAGES : pipe_cfg<1>::STAGES;
+    const size_t smem = pipe_smem_bytes(threads, pipe_tpr(mean, hb_dtype_size(dtype)), stages, hb_dtype_size(dtype));
+    int by_smem = (int) ((227 * 1024) / (smem + 1024 + 512));        // + per-CTA reservation + static shared
+    int by_thr = threads >= 256 ? 3 : 6;                              // __launch_bounds__ minBlocks of the kernel (register budget)
+    int n = by_smem < by_thr ? by_smem : by_thr;
+    return n < 1 ? 1 : n;
+}
+
+template<typename T, int CFG, int TPR, bool DOT>
+static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    using C = pipe_cfg<CFG>;
+    const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
+    k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
+                                                            A->cta_rows[CFG], ctx->partials, ctx->tickets + 1, dot_out, skip);
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+template<typename T, int CFG, bool DOT>
+static int launch_pipe(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    switch (pipe_tpr(A->mean_row_nnz, sizeof(T))){
+        case 16: return launch_pipe_cfg<T, CFG, 16, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        case 8:  return launch_pipe_cfg<T, CFG, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        case 4:  return launch_pipe_cfg<T, CFG, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        case 2:  return launch_pipe_cfg<T, CFG, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        default: return launch_pipe_cfg<T, CFG, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    }
+}
+
+// resident CTAs per SM of the instantiation that will run (asked of the driver, not guessed): the persistent grid and its
+// partition table are sized from it at hb_csr_create time
+template<typename T, int CFG, int TPR, bool DOT>
+static int pipe_occupancy_one(){
+    using C = pipe_cfg<CFG>;
+    const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::THREADS, smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    return n;
+}
+template<typename T, int CFG>
+static int pipe_occupancy(int tpr){
+    int a = 0, b = 0;
+    switch (tpr){
+        case 16: a = pipe_occupancy_one<T, CFG, 16, false>(); b = pipe_occupancy_one<T, CFG, 16, true>(); break;
+        case 8:  a = pipe_occupancy_one<T, CFG, 8, false>();  b = pipe_occupancy_one<T, CFG, 8, true>();  break;
+        case 4:  a = pipe_occupancy_one<T, CFG, 4, false>();  b = pipe_occupancy_one<T, CFG, 4, true>();  break;
+        case 2:  a = pipe_occupancy_one<T, CFG, 2, false>();  b = pipe_occupancy_one<T, CFG, 2, true>();  break;
+        default: a = pipe_occupancy_one<T, CFG, 1, false>();  b = pipe_occupancy_one<T, CFG, 1, true>();  break;
+    }
+    return a < b ? a : b;
+}
+static int pipe_occupancy_any(int cfg, int tpr, int dtype){
+    HB_DISPATCH(dtype, { return cfg == 0 ? pipe_occupancy<T, 0>(tpr) : pipe_occupancy<T, 1>(tpr); });
+    return 0;
+}
+
+// variant: 0 auto, 1 row-vector, 2 staged tiles, 3 streaming pipeline (bulk-async ring)
 template<typename T, bool DOT>
 int hb_spmv_n_typed(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
     int variant = A->variant;
     const double mean = A->mean_row_nnz;
-    if (variant == 0 || variant == 3) variant = (mean > 96.0) ? 1 : 2;
+    const bool pipe_ok = A->vec_aligned && A->cta_rows[A->pipe_cfg] != nullptr && A->nnz > 0;
+    if (variant == 0) variant = (mean > 112.0) ? 1 : (pipe_ok ? 3 : 2);
+    if (variant == 3 && !pipe_ok) variant = 2;
+    if (variant == 3){
+        if (A->pipe_cfg == 0) return launch_pipe<T, 0, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        return launch_pipe<T, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    }
     if (variant == 2){
         if (mean >= 16.0) return launch_tiles<T, 128, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         return launch_tiles<T, 256, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
     }
-    if (mean > 48.0)      return launch_rowvec<T, 32, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
-    else if (mean > 20.0) return launch_rowvec<T, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
-    else if (mean > 6.0)  return launch_rowvec<T, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    // TPR * RV_UNR slots per step: pick the smallest TPR whose single step covers a typical row
+    if (mean > 64.0)      return launch_rowvec<T, 32, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    else if (mean > 16.0) return launch_rowvec<T, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    else if (mean > 8.0)  return launch_rowvec<T, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
     return launch_rowvec<T, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
 }
 
@@ -325,13 +423,37 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
         csr_analyse_kernel<<<grid, 256, 0, ctx->stream>>>(rows, pntr, A->stats_dev);
         HB_LAUNCH_CHECK(ctx);
     }
+    // equal-nnz row partition tables for the streaming kernel (one per pipeline configuration)
+    const char *cfg_env = getenv("HB_PIPE_CFG");
+    A->pipe_cfg = (cfg_env && cfg_env[0] == '1') ? 1 : 0;
+    A->vec_aligned = A->vec_aligned && aligned16p(pntr);
+    if (rows > 0 && nnz > 0 && A->vec_aligned){
+        for (int c = 0; c < 2; c++){
+            const int threads = c == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
+            const int tile_rows = threads / pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype));
+            const int ntiles = (rows + tile_rows - 1) / tile_rows;
+            const int occ = pipe_occupancy_any(c, pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype)), dtype);
+            if (occ < 1) continue;                          // this configuration cannot run here: cta_rows stays null
+            int G = ctx->num_sms * occ;
+            if (G > ntiles) G = ntiles;
+            A->pipe_grid[c] = G;
+            HB_CUDA(cudaMalloc((void**) &A->cta_rows[c], sizeof(int) * (size_t) (G + 1)));
+            csr_partition_kernel<<<(G + 1 + 127) / 128, 128, 0, ctx->stream>>>(rows, nnz, pntr, tile_rows, G, A->cta_rows[c]);
+            HB_LAUNCH_CHECK(ctx);
+        }
+    }
     HB_CUDA(cudaMemcpyAsync(&A->max_row_nnz, A->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = A;
     return HB_OK;
 }
 
-int hb_csr_destroy(hb_csr *csr){ delete csr; return HB_OK; }
+int hb_csr_destroy(hb_csr *csr){
+    if (!csr) return HB_OK;
+    for (int c = 0; c < 2; c++) if (csr->cta_rows[c]) cudaFree(csr->cta_rows[c]);
+    delete csr;
+    return HB_OK;
+}
 
 int hb_csr_info(const hb_csr *A, int *dtype, int *rows, int *cols, int *nnz, int *max_row_nnz){
     HB_ARG(A, "csr is null");

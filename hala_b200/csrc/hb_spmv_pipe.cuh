@@ -1,0 +1,232 @@
+// hb_spmv_pipe.cuh — the streaming CSR SpMV kernel: persistent CTAs, bulk-async (TMA engine) staging of the CSR stream
+// into a shared-memory ring, sub-warp-per-row consumption.
+//
+// Why: a CSR row-vector kernel saturates the L1TEX tag stage long before HBM — every warp-level load of values/col_idx
+// touches 4-5 cache lines because rows are 27*8 B apart (ncu: l1tex 68 %, DRAM 45 % on the 27-point Laplacian).  Here
+// the matrix stream never enters L1TEX: it goes HBM -> L2 -> shared memory through cp.async.bulk (SASS: UBLKCP), and
+// L1TEX is left with the only access that needs a cache, the gather of x.
+//
+// Work split: rows are cut into tiles of ROWS = THREADS/TPR consecutive rows; the tiles are cut into G contiguous pieces of
+// equal non-zero count once per matrix (tile table built by hb_csr_create); CTA g streams its piece.
+// Producer (thread 0): for tile t it issues three bulk copies into ring stage t % STAGES — the tile's slice of pntr, of
+// col_idx and of values (one contiguous range each) — completing on the stage's mbarrier, STAGES-1 tiles ahead of the
+// consumers; the two row-pointer bounds it needs are themselves read one step earlier, so the producer never waits.
+// Consumers (all threads): TPR lanes per row, lane l walks entries rs+l, rs+l+TPR, ... in batches of four
+// (all shared-memory reads, then all gathers, then the FMAs), shuffle-reduce, write y.  Adjacent lane groups own
+// adjacent rows, so on banded matrices one gather instruction touches 2-3 lines.  One __syncthreads per tile releases
+// the stage.  Tiles whose slice does not fit a stage (heavy-tailed row lengths) are processed straight from global
+// memory, long rows by the whole CTA.
+#pragma once
+#include "hb_common.cuh"
+
+// ring capacity per stage = THREADS * pipe_slots<T>() non-zeros; entries per lane per batch = the same number
+template<typename T> __host__ __device__ constexpr int pipe_slots(){ return sizeof(T) == 16 ? 4 : 8; }
+static constexpr int PIPE_LONGROW = 2048;       // slow path: rows at least this long are reduced by the whole CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p){ return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count){
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init(){ asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async(){ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes){
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity){
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar){
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src){
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit(){ asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all(){ asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// cta_tiles[g] = first tile t (of `tile_rows` rows) whose first non-zero index is >= g*nnz/G ; cta_tiles[G] = ntiles
+__global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int tile_rows, int G, int *cta_tiles){
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G) return;
+    const int ntiles = (rows + tile_rows - 1) / tile_rows;
+    if (g == G){ cta_tiles[g] = ntiles; return; }
+    const long long target = (long long) nnz * g / G;
+    int lo = 0, hi = ntiles;
+    while (lo < hi){
+        int mid = lo + ((hi - lo) >> 1);
+        if (pntr[(long long) mid * tile_rows] >= target) hi = mid; else lo = mid + 1;
+    }
+    cta_tiles[g] = lo;
+}
+
+template<typename T, int THREADS, int TPR, int STAGES, bool DOT>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
+                                                            const T * __restrict__ vals, const T * __restrict__ x, T *y,
+                                                            scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
+                                                            void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag){
+    constexpr int ROWS = THREADS / TPR;
+    constexpr int CAP  = THREADS * pipe_slots<T>();
+    constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
+    constexpr int PSL  = ROWS + 4;                          // ints of the pntr slice per stage
+    constexpr size_t STAGE_BYTES = (size_t) (CAP + 4) * (sizeof(T) + sizeof(int)) + PSL * sizeof(int);
+    static_assert(STAGE_BYTES % 16 == 0, "stage must stay 16-byte aligned");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[STAGES];
+    constexpr int BND = 64;
+    __shared__ int      bnd[BND];
+    __shared__ int      stage_a0[STAGES];                   // first staged non-zero index of the tile, or -1: not staged (slow path)
+    __shared__ T        red[32];
+
+    if (skip_flag && *skip_flag) return;
+
+    const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    const int tile_begin = cta_tiles[blockIdx.x], tile_end = cta_tiles[blockIdx.x + 1];
+    const int ntile = tile_end - tile_begin;
+    const int nnz4 = nnz & ~3, np4 = (rows + 1) & ~3;
+    T dot_acc = zero_of<T>();
+
+    auto stage_vals = [&](int s){ return reinterpret_cast<T*>(smem_raw + (size_t) s * STAGE_BYTES); };
+    auto stage_cols = [&](int s){ return reinterpret_cast<int*>(smem_raw + (size_t) s * STAGE_BYTES + (size_t) (CAP + 4) * sizeof(T)); };
+    auto stage_ptr  = [&](int s){ return reinterpret_cast<int*>(smem_raw + (size_t) s * STAGE_BYTES + (size_t) (CAP + 4) * (sizeof(T) + sizeof(int))); };
+
+    if (ntile > 0){
+        if (tid == 0){
+            for (int s = 0; s < STAGES; s++) mbar_init(full + s, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+
+        // Tile bounds ring: bnd[j % BND] = pntr[first row of local tile j] (j == ntile: end of the piece).  The producer needs
+        // two of them per issue; a dependent global load there would put a DRAM round trip on every step's critical path
+        // (all warps meet at the per-step barrier), so the ring is refilled 32 entries at a time with cp.async by the last
+        // warp, a whole 16 steps before the data is waited for and 30 before it is used.
+        auto bound_src = [&](int j){ return pntr + min((long long) (tile_begin + j) * ROWS, (long long) rows); };
+        for (int j = tid; j < BND && j <= ntile; j += THREADS) bnd[j] = __ldg(bound_src(j));
+        __syncthreads();
+        auto issue = [&](int k, int b0, int b1){             // thread 0 only; b0,b1 = non-zero bounds of tile k
+            const int s = k % STAGES;
+            const int r0 = (tile_begin + k) * ROWS;
+            T *sv = stage_vals(s); int *sc = stage_cols(s); int *sp = stage_ptr(s);
+            // pntr slice [r0, r0 + PSL) clipped to the array; ragged end by hand
+            const int pend = min(r0 + PSL, rows + 1);
+            const int pbulk_end = min(pend & ~3, np4);
+            const int npb = max(pbulk_end - r0, 0);
+            for (int e = r0 + npb; e < pend; e++) sp[e - r0] = pntr[e];
+            const int a0 = b0 & ~3;
+            const bool fits = (b1 - a0) <= CAP;
+            uint32_t bytes = (uint32_t) (npb * sizeof(int));
+            int nb = 0;
+            if (fits){
+                const int cend4 = (b1 + 3) & ~3;
+                const int bulk_end = min(cend4, nnz4);
+                nb = max(bulk_end - a0, 0);
+                for (int e = a0 + nb; e < min(cend4, nnz); e++){ sv[e - a0] = vals[e]; sc[e - a0] = indx[e]; }
+                bytes += (uint32_t) (nb * (sizeof(T) + sizeof(int)));
+            }
+            stage_a0[s] = fits ? a0 : -1;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(full + s, bytes);
+            if (npb > 0) bulk_g2s(sp, pntr + r0, (uint32_t) (npb * sizeof(int)), full + s);
+            if (nb > 0){
+                bulk_g2s(sv, vals + a0, (uint32_t) (nb * sizeof(T)), full + s);
+                bulk_g2s(sc, indx + a0, (uint32_t) (nb * sizeof(int)), full + s);
+            }
+        };
+        if (tid == 0) for (int k = 0; k < STAGES - 1 && k < ntile; k++) issue(k, bnd[k % BND], bnd[(k + 1) % BND]);
+
+        for (int k = 0; k < ntile; k++){
+            const int s = k % STAGES;
+            if (tid == 0 && k + STAGES - 1 < ntile) issue(k + STAGES - 1, bnd[(k + STAGES - 1) % BND], bnd[(k + STAGES) % BND]);
+            if (tid >= THREADS - 32){                           // ring refill by the last warp (see above)
+                if ((k & 31) == 0 && k > 0){
+                    const int j = k + 32 + (tid & 31);
+                    if (j <= ntile) cp_async4(&bnd[j % BND], bound_src(j));
+                    cp_async_commit();
+                }else if ((k & 31) == 16){
+                    cp_async_wait_all();                        // published to thread 0 by this step's closing barrier
+                }
+            }
+            mbar_wait(full + s, (uint32_t) ((k / STAGES) & 1));
+            const int r0 = (tile_begin + k) * ROWS;
+            const int myrow = r0 + grp;
+            const int *sp = stage_ptr(s);
+            const int a0 = stage_a0[s];
+            int rs = 0, re = 0;
+            if (myrow < rows){ rs = sp[grp]; re = sp[grp + 1]; }
+            T sum = zero_of<T>();
+            if (a0 >= 0){
+                const T *sv = stage_vals(s); const int *sc = stage_cols(s);
+                // batches of PIPE_UNR entries per lane: all shared-memory reads, then all gathers, then the FMAs (two
+                // accumulators), so one row of up to PIPE_UNR*TPR entries costs a single gather round trip
+                const int end = re - a0;
+                T sum2 = zero_of<T>();
+                for (int base = rs + sub - a0; base < end; base += PIPE_UNR * TPR){
+                    int c[PIPE_UNR]; T v[PIPE_UNR], xv[PIPE_UNR]; bool ok[PIPE_UNR];
+                    #pragma unroll
+                    for (int u = 0; u < PIPE_UNR; u++){
+                        ok[u] = (base + u * TPR) < end;
+                        if (ok[u]){ c[u] = sc[base + u * TPR]; v[u] = sv[base + u * TPR]; }
+                    }
+                    #pragma unroll
+                    for (int u = 0; u < PIPE_UNR; u++) if (ok[u]) xv[u] = ld_ro(x + c[u]);
+                    #pragma unroll
+                    for (int u = 0; u < PIPE_UNR; u += 2){
+                        if (ok[u]) sum = hfma(v[u], xv[u], sum);
+                        if (ok[u + 1]) sum2 = hfma(v[u + 1], xv[u + 1], sum2);
+                    }
+                }
+                sum = hadd(sum, sum2);
+            }else{
+                // slice larger than a stage: straight from global memory; very long rows by the whole CTA
+                if (re - rs < PIPE_LONGROW)
+                    for (int j = rs + sub; j < re; j += TPR) sum = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), sum);
+                const int rlast = min(r0 + ROWS, rows);
+                for (int r = r0; r < rlast; r++){
+                    const int ls = sp[r - r0], le = sp[r - r0 + 1];
+                    if (le - ls < PIPE_LONGROW) continue;       // block-uniform: sp is shared
+                    T part = zero_of<T>();
+                    for (int j = ls + tid; j < le; j += THREADS) part = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), part);
+                    part = block_sum(part, red);                // contains __syncthreads; result in thread 0
+                    if (tid == 0) red[0] = part;
+                    __syncthreads();
+                    if (myrow == r && sub == 0) sum = red[0];
+                    __syncthreads();
+                }
+            }
+            #pragma unroll
+            for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
+            if (sub == 0 && myrow < rows){
+                if (DOT){
+                    y[myrow] = sum;
+                    dot_acc = hfma(hconj(ld_ro(x + myrow)), sum, dot_acc);
+                }else{
+                    T out = hmul(alpha, sum);
+                    if (use_beta) out = hfma(beta, y[myrow], out);
+                    y[myrow] = out;
+                }
+            }
+            __syncthreads();                                    // stage s may be refilled
+        }
+    }
+    if (DOT){
+        T *partials = reinterpret_cast<T*>(partials_v);
+        T b = block_sum(dot_acc, red);
+        if (tid == 0) partials[blockIdx.x] = b;
+        if (last_block_arrives(ticket)){
+            T total = sum_partials<T>(partials, gridDim.x, 1, red);
+            if (tid == 0) *dot_out = total;
+        }
+    }
+}

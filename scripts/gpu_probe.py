@@ -19,7 +19,12 @@ except Exception:
     pass
 
 
-def timeit(e, fn, reps=20, warm=3):
+REPS, WARM = 20, 3
+
+
+def timeit(e, fn, reps=None, warm=None):
+    reps = REPS if reps is None else reps
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     e.timer_start()
@@ -36,10 +41,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c1,c2")
     ap.add_argument("--dtypes", default="f64")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--no-blas", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--variants", default="1,2,3")
     args = ap.parse_args()
+    global REPS, WARM
+    REPS, WARM = args.reps, args.warm
     e = hb.gpu_engine(0)
     # BLAS-1 streams, 64M doubles
-    n = 1 << 26
+    n = 1 << 26 if not args.no_blas else 1 << 10
     x, y = e.vector(n, 1.0), e.vector(n, 2.0)
     ms = timeit(e, lambda: hb.vcopy(e, x, y)); emit(op="copy", n=n, ms=ms, gbs=16 * n / ms / 1e6, frac=16 * n / ms / 1e6 / PEAK)
     ms = timeit(e, lambda: hb.axpy(e, 0.5, x, y)); emit(op="axpy", n=n, ms=ms, gbs=24 * n / ms / 1e6, frac=24 * n / ms / 1e6 / PEAK)
@@ -62,12 +74,14 @@ def main():
             A = hb.make_sparse_matrix(e, N, gp, gi, gv)
             gx, gy = e.load(mg.probe_x(N, dt)), e.new_vector(v.dtype, N)
             B = mg.spmv_bytes(N, nnz, v.dtype.itemsize)
-            for variant in (1, 2):
+            for variant in [int(t) for t in args.variants.split(",")]:
                 A.set_variant(variant)
                 ms = timeit(e, lambda: A.gemv("N", 1.0, gx, 0.0, gy))
                 emit(op="spmv", config=c, matrix=f"{name}:{size}", dtype=dt, variant=variant, N=N, nnz=nnz, ms=ms, gbs=B / ms / 1e6,
                      frac_measured_peak=B / ms / 1e6 / PEAK, frac_8tbs=B / ms / 1e6 / 8000.0, gflops=2 * nnz / ms / 1e6, gen_s=gen_s)
             A.set_variant(0)
+            if args.no_cg:
+                continue
             gb = e.load(mg.rhs(N, dt))
             for iters in (200,):
                 gxx = e.new_vector(v.dtype)

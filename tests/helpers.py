@@ -44,6 +44,7 @@ def assert_entrywise(y, yref, scale, tol, what=""):
     assert np.all(err <= bound), f"{what}: worst scaled error {worst:.3e} > {tol:.1e}"
 
 
-def assert_reduction(val, ref, x, y, dt, what=""):
+def assert_reduction(val, ref, x, y, dt, what="", tol=None):
     scale = float(np.sum(np.abs(x).astype(np.float64) * np.abs(y).astype(np.float64)))
-    assert abs(complex(val) - complex(ref)) <= RED_TOL[dt] * max(scale, 1e-300), (what, val, ref)
+    tol = RED_TOL[dt] if tol is None else tol
+    assert abs(complex(val) - complex(ref)) <= tol * max(scale, 1e-300), (what, val, ref)

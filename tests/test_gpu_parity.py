@@ -89,7 +89,7 @@ def test_reference_solver_fixtures(engine, ref_tests, dt):
 
 
 # ------------------------------------------------------------------------------------------------ SpMV vs golden + oracle
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_spmv_matches_recorded_reference(engine, golden, variant):
     keys = [k for k in golden.files if k.startswith("spmv/")]
     for k in keys:
@@ -110,7 +110,7 @@ def test_spmv_matches_recorded_reference(engine, golden, variant):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_spmv_edge_shapes_vs_oracle(engine, orc, dt, variant):
     """Ragged and degenerate inputs: empty rows, a single row, rows longer than a staging chunk, unaligned base pointers,
     rectangular shapes, beta == 0 with NaN-filled y (y must not be read — cuSPARSE semantics)."""
@@ -183,7 +183,7 @@ def test_spmv_full_size_properties(engine, orc):
     gp, gi, gv = load_csr(engine, p, i, v)
     A = hb.make_sparse_matrix(engine, N, gp, gi, gv)
     x1, x2 = mg.probe_x(N, "f64", seed=7), mg.probe_x(N, "f64", seed=8)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         A.set_variant(variant)
         gy1, gy2, gy3 = (engine.new_vector(np.float64) for _ in range(3))
         A.gemv("N", 1.0, engine.load(x1), 0.0, gy1)
@@ -238,14 +238,21 @@ def test_blas1_sizes_vs_oracle(engine, orc, dt, n):
     x, y = mg.probe_x(n + 1, dt, seed=13), mg.probe_x(n + 1, dt, seed=14)
     a = -0.75 if dt in ("f32", "f64") else -0.75 + 0.25j
     rt = 2e-5 if "32" in dt else 1e-13
+    # the oracle sums serially in the data's own precision (its error grows like sqrt(n) * eps); the GPU reduces pairwise,
+    # nrm2 in double — so against the serial oracle the bound has to carry that growth
+    eps = 6e-8 if "32" in dt else 1.1e-16
+    red = max(RED_TOL[dt], 8.0 * np.sqrt(max(n, 1)) * eps)
     for off in (0, 1):
         xs, ys = x[off:off + n], y[off:off + n]
         gx_full, gy_full = engine.load(x), engine.load(y)
         gx, gy = _view(engine, gx_full, off, n), _view(engine, gy_full, off, n)
         if n:
-            assert_reduction(hb.dot(engine, gx, gy, N=n), orc.blas1("dot", xs, ys), xs, ys, dt)
-            assert_reduction(hb.dotu(engine, gx, gy, N=n), orc.blas1("dotu", xs, ys), xs, ys, dt)
-            np.testing.assert_allclose(hb.norm2(engine, gx, N=n), orc.blas1("nrm2", xs), rtol=RED_TOL[dt])
+            assert_reduction(hb.dot(engine, gx, gy, N=n), orc.blas1("dot", xs, ys), xs, ys, dt, "dot", red)
+            assert_reduction(hb.dotu(engine, gx, gy, N=n), orc.blas1("dotu", xs, ys), xs, ys, dt, "dotu", red)
+            assert_reduction(hb.dot(engine, gx, gy, N=n), np.vdot(xs.astype(np.complex128), ys.astype(np.complex128)), xs, ys, dt, "dot64")
+            np.testing.assert_allclose(hb.norm2(engine, gx, N=n), orc.blas1("nrm2", xs), rtol=red)
+            # and tightly against a float64 evaluation of the same data
+            np.testing.assert_allclose(hb.norm2(engine, gx, N=n), np.linalg.norm(xs.astype(np.complex128)), rtol=RED_TOL[dt])
         else:
             assert hb.dot(engine, gx, gy, N=0) == 0 and hb.norm2(engine, gx, N=0) == 0
         hb.axpy(engine, a, gx, gy, N=n)
@@ -369,14 +376,15 @@ def test_fused_pieces_vs_oracle(engine, orc):
         a = 0.3 if dt in ("f32", "f64") else 0.3 - 0.2j
         ga = engine.load(np.array([a], dtype=NP[dt]))
         gxx, grr, gout = engine.load(xv), engine.load(rv), engine.new_vector(NP[dt], 1)
-        check(lib.hb_axpy2_nrm2(engine.ctx, code, N, ga.ptr, engine.load(pv).ptr, engine.load(qv).ptr, gxx.ptr, grr.ptr, gout.ptr))
+        gpv, gqv = engine.load(pv), engine.load(qv)          # keep the device arrays alive across the asynchronous call
+        check(lib.hb_axpy2_nrm2(engine.ctx, code, N, ga.ptr, gpv.ptr, gqv.ptr, gxx.ptr, grr.ptr, gout.ptr))
         rt = 1e-5 if "32" in dt else 1e-13
         rnew = rv - NP[dt](a) * qv
         np.testing.assert_allclose(gxx.unload(), xv + NP[dt](a) * pv, rtol=rt, atol=rt)
         np.testing.assert_allclose(grr.unload(), rnew, rtol=rt, atol=rt)
         np.testing.assert_allclose(gout.unload()[0].real, np.vdot(rnew, rnew).real, rtol=20 * rt)
-        gpp = engine.load(pv)
-        check(lib.hb_xpby(engine.ctx, code, N, engine.load(rv).ptr, ga.ptr, gpp.ptr))
+        gpp, grv = engine.load(pv), engine.load(rv)
+        check(lib.hb_xpby(engine.ctx, code, N, grv.ptr, ga.ptr, gpp.ptr))
         np.testing.assert_allclose(gpp.unload(), rv + NP[dt](a) * pv, rtol=rt, atol=rt)
         # multi-dot / multi-axpy on a 9-column basis
         K = 9
