@@ -23,7 +23,12 @@ struct hb_ctx {
     void *hscalars = nullptr;           // pinned, device-mapped host page for scalar read-back
     void *hscalars_dev = nullptr;       // device alias of hscalars
     cudaEvent_t timer[2] = {nullptr, nullptr};
+    // solver workspace, grown on demand and kept across solves (the reference pays a cudaMalloc per new_vector per solve;
+    // here a second solve of the same size allocates nothing).  Released by hb_ctx_trim / hb_ctx_destroy.
+    void  *work = nullptr;
+    size_t work_bytes = 0;
 };
+int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr);
 
 static constexpr size_t HB_PARTIAL_BYTES = 4u << 20;   // 4 MiB: (blocks x up-to-64 columns x 16 B) fits for grid <= 4096
 static constexpr int    HB_NUM_TICKETS   = 64;

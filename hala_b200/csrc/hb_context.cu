@@ -15,6 +15,17 @@ template<typename T> __global__ void fill_kernel(size_t n, T value, T *x){
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) x[i] = value;
 }
 
+int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr){
+    if (bytes > ctx->work_bytes){
+        if (ctx->work){ HB_CUDA(cudaStreamSynchronize(ctx->stream)); HB_CUDA(cudaFree(ctx->work)); ctx->work = nullptr; ctx->work_bytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->work, bytes);
+        if (e != cudaSuccess){ hb_cuda_fail(e, "solver workspace cudaMalloc"); return HB_ERR_ALLOC; }
+        ctx->work_bytes = bytes;
+    }
+    *ptr = ctx->work;
+    return HB_OK;
+}
+
 extern "C" {
 
 const char* hb_version(void){ return "halab200 0.1 (sm_100a)"; }
@@ -57,11 +68,17 @@ int hb_ctx_destroy(hb_ctx *ctx){
     cudaSetDevice(ctx->device);
     if (ctx->timer[0]) cudaEventDestroy(ctx->timer[0]);
     if (ctx->timer[1]) cudaEventDestroy(ctx->timer[1]);
+    if (ctx->work) cudaFree(ctx->work);
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->dscalars); cudaFreeHost(ctx->hscalars);
     delete ctx;
     return HB_OK;
 }
 
+int hb_ctx_trim(hb_ctx *ctx){
+    HB_ARG(ctx, "ctx is null");
+    if (ctx->work){ HB_CUDA(cudaFree(ctx->work)); ctx->work = nullptr; ctx->work_bytes = 0; }
+    return HB_OK;
+}
 int hb_ctx_device(const hb_ctx *ctx, int *device){ HB_ARG(ctx && device, "null"); *device = ctx->device; return HB_OK; }
 int hb_ctx_set_stream(hb_ctx *ctx, void *s){ HB_ARG(ctx, "ctx is null"); ctx->stream = (cudaStream_t) s; return HB_OK; }
 int hb_ctx_get_stream(const hb_ctx *ctx, void **s){ HB_ARG(ctx && s, "null"); *s = (void*) ctx->stream; return HB_OK; }

@@ -96,12 +96,14 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
     using R = real_t<T>;
     const int n = A->rows;
     const R tol = (R) tol_d;
-    dev_buffer tbuf, wbuf, hbuf;
     int rc;
-    if ((rc = tbuf.alloc(sizeof(T) * (size_t) n)) != HB_OK) return rc;
-    if ((rc = wbuf.alloc(sizeof(T) * (size_t) n * (size_t) restart)) != HB_OK) return rc;
-    if ((rc = hbuf.alloc(sizeof(T) * (size_t) (restart + 2))) != HB_OK) return rc;
-    T *t = (T*) tbuf.p, *W = (T*) wbuf.p, *hdev = (T*) hbuf.p;
+    // workspace: t | W (n x restart, column-major) | h (restart + 2 scalars), from the context's cached arena
+    const size_t vec_bytes = ((sizeof(T) * (size_t) n + 255) / 256) * 256;
+    void *arena = nullptr;
+    if ((rc = hb_ctx_workspace(ctx, vec_bytes * ((size_t) restart + 1) + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
+    T *t = (T*) arena, *W = (T*) ((char*) arena + vec_bytes);
+    T *hdev = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 1));
+    const size_t ldw = vec_bytes / sizeof(T);
     T *hhost = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->hscalars) + 1024);   // pinned staging, (restart+2) scalars <= 3 KiB
     HB_ARG((size_t) (restart + 2) * sizeof(T) <= HB_SCALAR_BYTES - 1024, "restart too large for the pinned staging area (max 190)");
     const int saved_mode = ctx->pointer_mode;
@@ -130,12 +132,12 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
 
         int inner = 0;
         while ((inner_res > tol) && (inner < restart)){
-            const T *wj = W + (size_t) inner * n;
+            const T *wj = W + (size_t) inner * ldw;
             if ((rc = hb_spmv_internal(ctx, A, wj, t, nullptr)) != HB_OK) return rc;                         // t = A w_j ; r = P^-1 t
             total++;
             const int k = inner + 1;
-            if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, (size_t) n, t, hdev, nullptr)) != HB_OK) return rc;
-            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, (size_t) n, hdev, t, hdev + k, -1.0, nullptr)) != HB_OK) return rc;
+            if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, ldw, t, hdev, nullptr)) != HB_OK) return rc;
+            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, ldw, hdev, t, hdev + k, -1.0, nullptr)) != HB_OK) return rc;
             HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T) * (size_t) (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
             HB_CUDA(cudaStreamSynchronize(ctx->stream));
             coeffs.assign(hhost, hhost + k);
@@ -150,7 +152,7 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
             inner_res = habs(hmul(S.back(), Z.back()));
             inner++;
             if ((inner_res > tol) && (inner < restart)){
-                if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev + k, W + (size_t) inner * n, nullptr)) != HB_OK) return rc;
+                if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev + k, W + (size_t) inner * ldw, nullptr)) != HB_OK) return rc;
                 Z.push_back(zero_of<T>());
                 h_rot(Z[inner - 1], Z[inner], C.back(), S.back());
             }
@@ -160,7 +162,7 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
             h_tpsv_unn(nz, H, Z);
             memcpy(hhost, Z.data(), sizeof(T) * (size_t) nz);
             HB_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(T) * (size_t) nz, cudaMemcpyHostToDevice, ctx->stream));
-            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, nz, W, (size_t) n, hdev, x, nullptr, 1.0, nullptr)) != HB_OK) return rc;
+            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, nz, W, ldw, hdev, x, nullptr, 1.0, nullptr)) != HB_OK) return rc;
             HB_CUDA(cudaStreamSynchronize(ctx->stream));      // hhost is reused by the next outer iteration
         }
         outer++;
@@ -182,12 +184,12 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
     const int n = A->rows, dtype = A->dtype;
     const size_t es = hb_dtype_size(dtype);
     if (n == 0){ if (iters) *iters = 1; if (res) *res = 0; return HB_OK; }
-    dev_buffer work;
     int rc;
-    // r | p | Ap | state
+    // r | p | Ap | state, from the context's cached arena
     const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256;
-    if ((rc = work.alloc(3 * vec_bytes + 256)) != HB_OK) return rc;
-    char *base = (char*) work.p;
+    void *arena = nullptr;
+    if ((rc = hb_ctx_workspace(ctx, 3 * vec_bytes + 256, &arena)) != HB_OK) return rc;
+    char *base = (char*) arena;
     void *r = base, *p = base + vec_bytes, *Ap = base + 2 * vec_bytes, *state = base + 3 * vec_bytes;
     void *pap = (char*) state + hb_cg_state_pap_offset(dtype);
     const int *done_flag = reinterpret_cast<const int*>((char*) state + hb_cg_state_done_offset(dtype));

@@ -153,7 +153,7 @@ class gpu_engine:
 
 
 def _dptr(v):
-    return v.ptr if isinstance(v, gpu_vector) else v
+    return v.ptr if hasattr(v, "ptr") else v
 
 
 def _sc(value, dtype):

@@ -50,6 +50,7 @@ int hb_ctx_sync(hb_ctx *ctx);                                   /* gpu_engine::s
 int hb_ctx_set_pointer_mode(hb_ctx *ctx, int mode);             /* set/reset_blas_device_pntr (:105-111) */
 int hb_ctx_get_pointer_mode(const hb_ctx *ctx, int *mode);      /* get_blas_pointer_mode (:112-117) */
 int hb_ctx_launch_count(const hb_ctx *ctx, long long *count);   /* kernels launched through this context so far */
+int hb_ctx_trim(hb_ctx *ctx);                                   /* frees the cached solver workspace (kept across hb_cg / hb_gmres calls) */
 
 /* ---- device timers (CUDA events on the context stream) — measurement plumbing for bench.py; the reference only has the
  *      wall-clock hala::chronometer (common/hala_core.hpp:155-162) ---- */
