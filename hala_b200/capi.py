@@ -43,6 +43,10 @@ SIGNATURES = {
     "hb_memcpy_async": (_i, [_vp, _vp, _vp, _sz, _i]),
     "hb_memset_zero": (_i, [_vp, _vp, _sz]),
     "hb_fill": (_i, [_vp, _i, _sz, _vp, _vp]),
+    "hb_dev_malloc": (_i, [_i, _sz, _pvp]),
+    "hb_dev_free": (_i, [_vp]),
+    "hb_dev_memcpy": (_i, [_vp, _vp, _sz, _i]),
+    "hb_dev_fill": (_i, [_i, _i, _sz, _vp, _vp]),
     "hb_host_alloc": (_i, [_sz, _pvp]),
     "hb_host_free": (_i, [_vp]),
     "hb_csr_create": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _pvp]),
@@ -57,6 +61,7 @@ SIGNATURES = {
     "hb_scal": (_i, [_vp, _i, _i, _vp, _vp, _i]),
     "hb_dot": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "hb_nrm2": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "hb_asum": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hb_gemv": (_i, [_vp, _i, C.c_char, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]),
     "hb_multi_dot": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "hb_multi_axpy_nrm2": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _vp]),

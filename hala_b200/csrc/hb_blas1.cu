@@ -90,13 +90,19 @@ template<typename T> __global__ void __launch_bounds__(B1_THREADS) scal_vec(size
 }
 
 // ---------------------------------------------------------------- reductions
-// MODE 0: dot (unconjugated), 1: dot (conj(x) * y), 2: sum |x|^2 accumulated in double (nrm2; y unused)
+// MODE 0: dot (unconjugated), 1: dot (conj(x) * y), 2: sum |x|^2 accumulated in double (nrm2; y unused),
+// 3: sum |re| + |im| accumulated in double (asum; y unused)
 template<int MODE, typename T> struct red_type { using type = T; };
 template<typename T> struct red_type<2, T> { using type = double; };
+template<typename T> struct red_type<3, T> { using type = double; };
+__device__ __forceinline__ double habs1(float a){ return fabs((double) a); }
+__device__ __forceinline__ double habs1(double a){ return fabs(a); }
+template<typename R> __device__ __forceinline__ double habs1(cplx<R> a){ return fabs((double) a.re) + fabs((double) a.im); }
 
 template<int MODE, typename T>
 __device__ __forceinline__ typename red_type<MODE, T>::type red_term(T a, T b, typename red_type<MODE, T>::type acc){
     if constexpr (MODE == 2) return acc + (double) habs2(a);
+    else if constexpr (MODE == 3) return acc + habs1(a);
     else if constexpr (MODE == 1) return hfma(hconj(a), b, acc);
     else return hfma(a, b, acc);
 }
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(B1_THREADS) reduce_kernel(int n, size_t nvec, 
         for (; i + (B1_UNROLL - 1) * stride < nvec; i += B1_UNROLL * stride){
             vec16<T> a[B1_UNROLL], b[B1_UNROLL];
             #pragma unroll
-            for (int u = 0; u < B1_UNROLL; u++){ a[u] = vx[i + u * stride]; if (MODE != 2) b[u] = vy[i + u * stride]; else b[u] = a[u]; }
+            for (int u = 0; u < B1_UNROLL; u++){ a[u] = vx[i + u * stride]; if (MODE < 2) b[u] = vy[i + u * stride]; else b[u] = a[u]; }
             #pragma unroll
             for (int u = 0; u < B1_UNROLL; u++){
                 #pragma unroll
@@ -122,17 +128,17 @@ __global__ void __launch_bounds__(B1_THREADS) reduce_kernel(int n, size_t nvec, 
             }
         }
         for (; i < nvec; i += stride){
-            vec16<T> a = vx[i], b = (MODE != 2) ? vy[i] : a;
+            vec16<T> a = vx[i], b = (MODE < 2) ? vy[i] : a;
             #pragma unroll
             for (int k = 0; k < vec16<T>::N; k++) acc = red_term<MODE, T>(a.v[k], b.v[k], acc);
         }
         const long long done = (long long) nvec * vec16<T>::N;
         for (long long j = done + blockIdx.x * (long long) blockDim.x + threadIdx.x; j < n; j += (long long) gridDim.x * blockDim.x)
-            acc = red_term<MODE, T>(x[j], (MODE != 2) ? y[j] : x[j], acc);
+            acc = red_term<MODE, T>(x[j], (MODE < 2) ? y[j] : x[j], acc);
     }else{
         for (long long j = blockIdx.x * (long long) blockDim.x + threadIdx.x; j < n; j += (long long) gridDim.x * blockDim.x){
             T a = x[j * incx];
-            acc = red_term<MODE, T>(a, (MODE != 2) ? y[j * incy] : a, acc);
+            acc = red_term<MODE, T>(a, (MODE < 2) ? y[j * incy] : a, acc);
         }
     }
     A *partials = reinterpret_cast<A*>(partials_v);
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(B1_THREADS) reduce_kernel(int n, size_t nvec, 
         A total = sum_partials<A>(partials, gridDim.x, 1, red);
         if (threadIdx.x == 0){
             if constexpr (MODE == 2) *reinterpret_cast<real_t<T>*>(out_v) = (real_t<T>) sqrt(total);
+            else if constexpr (MODE == 3) *reinterpret_cast<real_t<T>*>(out_v) = (real_t<T>) total;
             else *reinterpret_cast<T*>(out_v) = total;
         }
     }
@@ -149,14 +156,14 @@ __global__ void __launch_bounds__(B1_THREADS) reduce_kernel(int n, size_t nvec, 
 
 template<int MODE, typename T>
 static int launch_reduce(hb_ctx *ctx, int n, const T *x, int incx, const T *y, int incy, void *result){
-    const size_t out_bytes = (MODE == 2) ? sizeof(real_t<T>) : sizeof(T);
+    const size_t out_bytes = (MODE >= 2) ? sizeof(real_t<T>) : sizeof(T);
     void *out = (ctx->pointer_mode == HB_POINTER_HOST) ? ctx->hscalars_dev : result;
     if (n <= 0){
         if (ctx->pointer_mode == HB_POINTER_HOST) memset(result, 0, out_bytes);
         else HB_CUDA(cudaMemsetAsync(result, 0, out_bytes, ctx->stream));
         return HB_OK;
     }
-    const bool vec = (incx == 1) && (MODE == 2 || incy == 1) && aligned16(x) && (MODE == 2 || aligned16(y));
+    const bool vec = (incx == 1) && (MODE >= 2 || incy == 1) && aligned16(x) && (MODE >= 2 || aligned16(y));
     const size_t nvec = vec ? (size_t) n / vec16<T>::N : 0;
     // when the vector path leaves nothing (n < N) fall back to the element-wise loop
     const size_t use_nvec = (nvec > 0) ? nvec : 0;
@@ -253,6 +260,13 @@ int hb_dot(hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, con
         if (conj && is_cplx<T>::value) return launch_reduce<1, T>(ctx, n, (const T*) x, incx, (const T*) y, incy, result);
         return launch_reduce<0, T>(ctx, n, (const T*) x, incx, (const T*) y, incy, result);
     });
+    return HB_OK;
+}
+
+int hb_asum(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result){
+    HB_ARG(ctx && result, "null");
+    HB_ARG(n <= 0 || x, "null vector");
+    HB_DISPATCH(dtype, { return launch_reduce<3, T>(ctx, n, (const T*) x, incx, (const T*) x, incx, result); });
     return HB_OK;
 }
 

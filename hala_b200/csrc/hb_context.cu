@@ -2,6 +2,7 @@
 // Replaces: gpu_engine handle management (reference gpu/hala_gpu_engine.hpp:60-163), gpu_allocate/gpu_free/gpu_copy_n
 // (gpu/hala_cuda_common.hpp:253-330), gpu_vector::fill (gpu/hala_gpu_vector.hpp:147-156), set_zero (gpu_engine.hpp:335-352).
 #include "hb_common.cuh"
+#include <algorithm>
 
 static thread_local std::string g_last_error;
 
@@ -157,6 +158,36 @@ int hb_fill(hb_ctx *ctx, int dtype, size_t n, const void *host_value, void *x){
         HB_DISPATCH(dtype, (fill_kernel<T><<<grid, 256, 0, ctx->stream>>>(n, *(const T*) host_value, (T*) x)));
     }
     HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_dev_malloc(int device, size_t bytes, void **ptr){
+    HB_ARG(ptr, "null");
+    HB_CUDA(cudaSetDevice(device));
+    *ptr = nullptr;
+    if (bytes == 0) return HB_OK;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess){ hb_cuda_fail(e, "hb_dev_malloc"); return HB_ERR_ALLOC; }
+    return HB_OK;
+}
+int hb_dev_free(void *ptr){ if (ptr) HB_CUDA(cudaFree(ptr)); return HB_OK; }
+int hb_dev_memcpy(void *dst, const void *src, size_t bytes, int kind){
+    if (bytes == 0) return HB_OK;
+    HB_CUDA(cudaMemcpy(dst, src, bytes, to_kind(kind)));
+    return HB_OK;
+}
+int hb_dev_fill(int device, int dtype, size_t n, const void *host_value, void *x){
+    HB_ARG(host_value, "null");
+    if (n == 0) return HB_OK;
+    HB_ARG(x, "x is null");
+    HB_CUDA(cudaSetDevice(device));
+    const int grid = (int) std::min<size_t>((n + 1023) / 1024, 148 * 8);
+    if (dtype == -1){
+        fill_kernel<int><<<grid, 256>>>(n, *(const int*) host_value, (int*) x);
+    }else{
+        HB_DISPATCH(dtype, (fill_kernel<T><<<grid, 256>>>(n, *(const T*) host_value, (T*) x)));
+    }
+    HB_CUDA(cudaPeekAtLastError());
+    HB_CUDA(cudaDeviceSynchronize());
     return HB_OK;
 }
 int hb_host_alloc(size_t bytes, void **ptr){

@@ -1,0 +1,130 @@
+#ifndef HALAB200_GPU_SPARSE_GENERAL_HPP
+#define HALAB200_GPU_SPARSE_GENERAL_HPP
+// gpu_sparse_matrix: non-owning CSR view + the one-time analysis of libhalab200 (hb_csr), in place of the cusparseSpMatDescr_t
+// wrapper of the reference (gpu/hala_cuda_sparse_general.hpp:191-375).  gemv -> hb_spmv; no per-call descriptors, no work
+// buffer (gemv_buffer_size is 0; a buffer argument is accepted and ignored so reference call sites compile unchanged).
+#include "hala_gpu_blas3.hpp"
+
+namespace hala{
+
+template<typename T>
+struct gpu_sparse_matrix{
+public:
+    using value_type = std::remove_cv_t<T>;
+    using engine_type = gpu_engine;
+
+    template<class VectorLikeP, class VectorLikeI, class VectorLikeV>
+    gpu_sparse_matrix(gpu_engine const &engine, int num_rows, int num_cols, int num_nz,
+                      VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals)
+        : rengine(engine), rows(num_rows), cols(num_cols), nnz(num_nz), handle(nullptr){
+        check_types(vals);
+        check_types_int(pntr, indx);
+        assert( check_size(pntr, rows+1) );
+        assert( check_size(indx, nnz) );
+        assert( check_size(vals, nnz) );
+        engine.check_gpu(pntr, indx, vals);
+        create(get_data(pntr), get_data(indx), get_standard_data(vals));
+    }
+    template<class VectorLikeP, class VectorLikeI, class VectorLikeV>
+    gpu_sparse_matrix(gpu_engine const &engine, int num_cols, VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals)
+        : rengine(engine), rows(get_size_int(pntr) - 1), cols(num_cols), nnz(get_size_int(indx)), handle(nullptr){
+        check_types(vals);
+        check_types_int(pntr, indx);
+        assert( check_size(vals, nnz) );
+        engine.check_gpu(pntr, indx, vals);
+        create(get_data(pntr), get_data(indx), get_standard_data(vals));
+    }
+    ~gpu_sparse_matrix(){ if (handle) hb_csr_destroy(handle); }
+
+    gpu_sparse_matrix(gpu_sparse_matrix const&) = delete;
+    gpu_sparse_matrix& operator = (gpu_sparse_matrix const&) = delete;
+    gpu_sparse_matrix(gpu_sparse_matrix &&other)
+        : rengine(other.rengine), rows(other.rows), cols(other.cols), nnz(other.nnz), handle(std::exchange(other.handle, nullptr)){}
+    gpu_sparse_matrix& operator = (gpu_sparse_matrix &&other){
+        if (this != &other){
+            if (handle) hb_csr_destroy(handle);
+            rows = other.rows; cols = other.cols; nnz = other.nnz; handle = std::exchange(other.handle, nullptr);
+        }
+        return *this;
+    }
+
+    gpu_engine const& engine() const{ return rengine; }
+    hb_csr* csr() const{ return handle; }
+
+    template<typename FPa, class VectorLikeX, typename FPb, class VectorLikeY>
+    size_t gemv_buffer_size(char trans, FPa, VectorLikeX const&, FPb beta, VectorLikeY &&y) const{
+        pntr_check_set_size(beta, y, (is_n(trans)) ? rows : cols, 1);
+        return 0;
+    }
+    template<typename FPa, class VectorLikeX, typename FPb, class VectorLikeY, class VectorLikeBuff>
+    void gemv(char trans, FPa alpha, VectorLikeX const &x, FPb beta, VectorLikeY &&y, VectorLikeBuff &&) const{
+        gemv(trans, alpha, x, beta, y);
+    }
+    template<typename FPa, class VectorLikeX, typename FPb, class VectorLikeY>
+    void gemv(char trans, FPa alpha, VectorLikeX const &x, FPb beta, VectorLikeY &&y) const{
+        check_types(x, y);
+        static_assert(std::is_same<get_standard_type<VectorLikeX>, typename define_standard_type<value_type>::value_type>::value
+                      || std::is_same<get_scalar_type<VectorLikeX>, value_type>::value, "vector type does not match the matrix");
+        rengine.check_gpu(x, y);
+        pntr_check_set_size(beta, y, (is_n(trans)) ? rows : cols, 1);
+        hb_scalar<value_type, FPa> a(alpha);
+        hb_scalar<value_type, FPb> b(beta);
+        check_hb(hb_spmv(rengine, handle, trans_to_hb<value_type>(trans), a.get(), get_data(x), b.get(), get_data(y)), "hala::gpu_sparse_matrix::gemv()");
+    }
+    // sparse matrix - dense matrix product (cusparseSpMM in the reference, :302-332) belongs to batch CG: SURVEY.md §8 row f2
+    template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC>
+    size_t gemm_buffer_size(char, char, int, int, FSA, VectorLikeB const&, int, FSB, VectorLikeC&, int) const{
+        HALAB200_OUT_OF_SCOPE(FSA, "hala::gpu_sparse_matrix::gemm()");
+        return 0;
+    }
+    template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC, class... Rest>
+    void gemm(char, char, int, int, FSA, VectorLikeB const&, int, FSB, VectorLikeC&, int, Rest&&...) const{
+        HALAB200_OUT_OF_SCOPE(FSA, "hala::gpu_sparse_matrix::gemm()");
+    }
+
+private:
+    void create(int const *p, int const *i, void const *v){
+        check_hb(hb_csr_create(rengine, hb_type<value_type>(), rows, cols, nnz, p, i, v, &handle), "hala::gpu_sparse_matrix()");
+    }
+    gpu_engine rengine;     // aliasing copy, as the reference holds (:369)
+    int rows, cols, nnz;
+    hb_csr *handle;
+};
+
+template<class VectorLikeP, class VectorLikeI, class VectorLikeV>
+auto make_sparse_matrix(gpu_engine const &engine, int num_rows, int num_cols, int num_nz,
+                        VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals){
+    check_types(vals);
+    check_types_int(pntr, indx);
+    using scalar_type = get_scalar_type<VectorLikeV>;
+    return gpu_sparse_matrix<scalar_type>(engine, num_rows, num_cols, num_nz, pntr, indx, vals);
+}
+template<class VectorLikeP, class VectorLikeI, class VectorLikeV>
+auto make_sparse_matrix(gpu_engine const &engine, int num_cols, VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals){
+    check_types(vals);
+    check_types_int(pntr, indx);
+    using scalar_type = get_scalar_type<VectorLikeV>;
+    return gpu_sparse_matrix<scalar_type>(engine, num_cols, pntr, indx, vals);
+}
+
+//! One-shot SpMV (reference :407-419): a temporary view per call; nnz is read from the size of indx.
+template<typename FPa, class VectorLikeP, class VectorLikeI, class VectorLikeV, class VectorLikeX, typename FPb, class VectorLikeY>
+void sparse_gemv(gpu_engine const &engine, char trans, int M, int N,
+                 FPa alpha, VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals, VectorLikeX const &x,
+                 FPb beta, VectorLikeY &y){
+    check_types(vals, x, y);
+    check_types_int(pntr, indx);
+    engine.check_gpu(pntr, indx, vals, x, y);
+    pntr_check_set_size(beta, y, (is_n(trans)) ? M : N, 1);
+    assert( valid::sparse_gemv(trans, M, N, 0, pntr, indx, vals, x, y) );
+    make_sparse_matrix(engine, M, N, get_size_int(indx), pntr, indx, vals).gemv(trans, alpha, x, beta, y);
+}
+
+template<typename FSA, class VectorLikeP, class VectorLikeI, class VectorLikeV, class VectorLikeB, typename FSB, class VectorLikeC>
+void sparse_gemm(gpu_engine const&, char, char, int, int, int, FSA, VectorLikeP const&, VectorLikeI const&, VectorLikeV const&,
+                 VectorLikeB const&, int, FSB, VectorLikeC&, int){
+    HALAB200_OUT_OF_SCOPE(FSA, "hala::sparse_gemm(gpu_engine)");
+}
+
+}
+#endif

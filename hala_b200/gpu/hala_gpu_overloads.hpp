@@ -1,0 +1,85 @@
+#ifndef HALAB200_GPU_OVERLOADS_HPP
+#define HALAB200_GPU_OVERLOADS_HPP
+// Default-argument overloads of the hot-path operations on gpu_engine (reference gpu/hala_gpu_overloads.hpp:69-128) and the
+// engine's vcopy member.  N defaults to 1 + (size - 1) / incx (valid::default_size), lda to M (valid::default_ld).
+#include "hala_gpu_plu.hpp"
+
+namespace hala{
+
+template<class vec>
+auto gpu_engine::vcopy(vec const &x) const{
+    auto y = new_vector(*this, x);
+    const int xdevice = get_device(x);
+    if ((xdevice > -1) && (xdevice != cgpu)){       // other device: through the host, as the reference does
+        using standard_type = get_standard_type<vec>;
+        std::vector<standard_type> cpuy(get_size(x));
+        gpu_copy_n<copy_direction::device2host>(reinterpret_cast<standard_type const*>(get_data(x)), get_size(x), get_data(cpuy));
+        y.load(cpuy);
+    }else{
+        hala::vcopy(*this, x, y);
+    }
+    return y;
+}
+
+template<class VectorLikeX> inline auto norm2(gpu_engine const &engine, VectorLikeX const &x, int incx = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    return norm2(engine, N, x, incx);
+}
+template<class VectorLikeX> inline auto asum(gpu_engine const &engine, VectorLikeX const &x, int incx = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    return asum(engine, N, x, incx);
+}
+template<bool conjugate = true, class VectorLikeX, class VectorLikeY>
+auto dot(gpu_engine const &engine, VectorLikeX const &x, VectorLikeY const &y, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    return dot<conjugate>(engine, N, x, incx, y, incy);
+}
+template<class VectorLikeX, class VectorLikeY>
+auto dotu(gpu_engine const &engine, VectorLikeX const &x, VectorLikeY const &y, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    return dot<false>(engine, N, x, incx, y, incy);
+}
+template<class VectorLikeX, class VectorLikeY>
+auto dotu(gpu_engine const &engine, int N, VectorLikeX const &x, int incx, VectorLikeY const &y, int incy){
+    return dot<false>(engine, N, x, incx, y, incy);
+}
+template<typename FP, class VectorLikeX, class VectorLikeY>
+void axpy(gpu_engine const &engine, FP alpha, VectorLikeX const &x, VectorLikeY &&y, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    axpy(engine, N, alpha, x, incx, y, incy);
+}
+template<typename FP, class VectorLike>
+void scal(gpu_engine const &engine, FP alpha, VectorLike &&x, int incx = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    scal(engine, N, alpha, x, incx);
+}
+template<typename FPA, typename FPB, class VectorLikeA, class VectorLikeX, class VectorLikeY>
+void gemv(gpu_engine const &engine, char trans, int M, int N,
+          FPA alpha, VectorLikeA const &A, VectorLikeX const &x, FPB beta, VectorLikeY &&y, int lda = -1, int incx = 1, int incy = 1){
+    valid::default_ld(M, lda);
+    gemv(engine, trans, M, N, alpha, A, lda, x, incx, beta, y, incy);
+}
+
+// names the wax templates mention with default arguments (batch helpers, SURVEY §8b gotcha 2): declared, out of scope on use
+template<typename FPa, class VectorLikeA, typename FPb, class VectorLikeB, class VectorLikeC>
+inline void geam(gpu_engine const &engine, char transa, char transb, int M, int N, FPa alpha, VectorLikeA const &A,
+                 FPb beta, VectorLikeB const &B, VectorLikeC &&C, int lda = -1, int ldb = -1, int ldc = -1){
+    geam(engine, transa, transb, M, N, alpha, A, lda, beta, B, ldb, C, ldc);
+}
+template<class VectorLikeA, class VectorLikeB, class VectorLikeC>
+inline void dgmm(gpu_engine const &engine, char side, int M, int N, VectorLikeA const &A,
+                 VectorLikeB const &x, VectorLikeC &&C, int lda = -1, int incx = 1, int ldc = -1){
+    dgmm(engine, side, M, N, A, lda, x, incx, C, ldc);
+}
+template<class VectorLikeX> inline int iamax(gpu_engine const &engine, VectorLikeX const &x, int incx = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    return iamax(engine, N, x, incx);
+}
+template<class VectorLikeA, class VectorLikeX>
+inline void tbsv(gpu_engine const &engine, char uplo, char trans, char diag, int N, int k, const VectorLikeA &A, VectorLikeX &&x, int lda = -1, int incx = 1){
+    valid::default_ld(k+1, lda);
+    tbsv(engine, uplo, trans, diag, N, k, A, lda, x, incx);
+}
+
+}
+#endif

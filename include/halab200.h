@@ -65,6 +65,11 @@ int hb_memcpy(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind); 
 int hb_memcpy_async(hb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);  /* on the context stream */
 int hb_memset_zero(hb_ctx *ctx, void *ptr, size_t bytes);
 int hb_fill(hb_ctx *ctx, int dtype, size_t n, const void *host_value, void *x);        /* dtype may also be -1: int32 */
+/* context-free variants on an explicit device id — what gpu_vector needs: it knows a device id, not an engine (gpu/hala_gpu_vector.hpp:49-171) */
+int hb_dev_malloc(int device, size_t bytes, void **ptr);
+int hb_dev_free(void *ptr);
+int hb_dev_memcpy(void *dst, const void *src, size_t bytes, int kind);                 /* host-synchronous, default stream */
+int hb_dev_fill(int device, int dtype, size_t n, const void *host_value, void *x);     /* gpu_vector::fill; dtype -1: int32; host-synchronous */
 int hb_host_alloc(size_t bytes, void **ptr);                                           /* pinned host memory */
 int hb_host_free(void *ptr);
 
@@ -91,6 +96,7 @@ int hb_axpy(hb_ctx *ctx, int dtype, int n, const void *alpha, const void *x, int
 int hb_scal(hb_ctx *ctx, int dtype, int n, const void *alpha, void *x, int incx);
 int hb_dot (hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, const void *y, int incy, void *result);
 int hb_nrm2(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result);
+int hb_asum(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result);   /* sum |re|+|im| (cublas?asum, gpu_blas1.hpp:124-143) */
 
 /* ---- BLAS-2 gemv, the Gram-Schmidt pair of GMRES: gpu/hala_gpu_blas2.hpp:39-62 (cublas?gemv), column-major A ---- */
 int hb_gemv(hb_ctx *ctx, int dtype, char trans, int M, int N, const void *alpha, const void *A, int lda,

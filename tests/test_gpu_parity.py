@@ -250,7 +250,8 @@ def test_blas1_sizes_vs_oracle(engine, orc, dt, n):
             assert_reduction(hb.dot(engine, gx, gy, N=n), orc.blas1("dot", xs, ys), xs, ys, dt, "dot", red)
             assert_reduction(hb.dotu(engine, gx, gy, N=n), orc.blas1("dotu", xs, ys), xs, ys, dt, "dotu", red)
             assert_reduction(hb.dot(engine, gx, gy, N=n), np.vdot(xs.astype(np.complex128), ys.astype(np.complex128)), xs, ys, dt, "dot64")
-            np.testing.assert_allclose(hb.norm2(engine, gx, N=n), orc.blas1("nrm2", xs), rtol=red)
+            if "64" in dt or n <= 65536:    # the serial float32 sum-of-squares of the oracle itself loses ~1e-3 beyond that
+                np.testing.assert_allclose(hb.norm2(engine, gx, N=n), orc.blas1("nrm2", xs), rtol=red)
             # and tightly against a float64 evaluation of the same data
             np.testing.assert_allclose(hb.norm2(engine, gx, N=n), np.linalg.norm(xs.astype(np.complex128)), rtol=RED_TOL[dt])
         else:
