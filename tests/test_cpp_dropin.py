@@ -42,6 +42,9 @@ def test_reference_tests_pass_on_the_b200_backend():
     if not os.path.exists(BIN):
         pytest.fail("tests/_bin/ref_tests_on_b200 missing: run __graft_entry__.build() in the build container first")
     env = dict(os.environ)
+    import sysconfig            # the wheel's OpenBLAS (CPU side of the comparison) needs its bundled libgfortran
+    blasdir = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
+    env["LD_LIBRARY_PATH"] = blasdir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     r = subprocess.run([BIN, "-v"], capture_output=True, text=True, timeout=300, env=env)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-4000:]
