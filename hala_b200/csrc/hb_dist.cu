@@ -1,0 +1,342 @@
+// hb_dist.cu — row-partitioned multi-GPU path: halo exchange, scalar all-reduce and the distributed CG iteration.
+// One process per GPU; NCCL (over NVLink 5 / NVSwitch) is loaded at run time.  New work: the reference is single-device.
+#include "hb_common.cuh"
+#include "../../include/halab200_dist.h"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <vector>
+
+int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
+int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
+
+// ------------------------------------------------------------------------------------------------ NCCL, resolved lazily
+namespace {
+struct nccl_api {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char*  (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+};
+nccl_api g_nccl;
+
+int load_nccl(){
+    if (g_nccl.lib) return HB_OK;
+    // RTLD_NOLOAD first: reuse the libnccl a host framework (e.g. torch) already mapped, then fall back to the system one
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h){ hb_set_error(std::string("cannot load libnccl.so.2: ") + dlerror()); return HB_ERR_NCCL; }
+    g_nccl.lib = h;
+    #define HB_SYM(field, name) do { *(void**) (&g_nccl.field) = dlsym(h, name); if (!g_nccl.field){ hb_set_error(std::string("libnccl lacks ") + name); g_nccl.lib = nullptr; return HB_ERR_NCCL; } } while (0)
+    HB_SYM(GetUniqueId, "ncclGetUniqueId"); HB_SYM(CommInitRank, "ncclCommInitRank"); HB_SYM(CommDestroy, "ncclCommDestroy");
+    HB_SYM(GetErrorString, "ncclGetErrorString"); HB_SYM(AllReduce, "ncclAllReduce"); HB_SYM(Send, "ncclSend"); HB_SYM(Recv, "ncclRecv");
+    HB_SYM(GroupStart, "ncclGroupStart"); HB_SYM(GroupEnd, "ncclGroupEnd");
+    #undef HB_SYM
+    return HB_OK;
+}
+int nccl_fail(ncclResult_t r, const char *what){
+    hb_set_error(std::string(what) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+    return HB_ERR_NCCL;
+}
+#define HB_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return nccl_fail(r__, #call); } while (0)
+}
+
+struct hb_dist {
+    hb_ctx *ctx = nullptr;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int n_owned = 0, n_ghost = 0;
+    std::vector<int> neigh, send_count, recv_count;
+    int send_total = 0;
+    const int *send_idx = nullptr;      // device, caller-owned
+    void *sendbuf = nullptr;            // device, send_total * 16 bytes
+    size_t sendbuf_bytes = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ kernels
+template<typename T> __global__ void pack_kernel(int n, const int * __restrict__ idx, const T * __restrict__ x, T *out){
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
+}
+
+// distributed CG state: every scalar that crosses a kernel boundary is double-buffered by iteration parity, so no kernel
+// reads a slot that another block of the same kernel writes
+template<typename T> struct cg_dstate {
+    T zr[2];
+    T pAp;              // local, then all-reduced in place
+    T rr;               // local ||r||^2 (as T, imaginary part 0), then all-reduced in place
+    double rnorm, tol;
+    int iterations, max_iter;
+    int done[2];
+};
+struct cg_dhost { volatile int done; volatile int iterations; volatile double rnorm; };
+
+static constexpr int DK_THREADS = 256;
+
+template<typename T>
+__global__ void __launch_bounds__(DK_THREADS) dcg_setup_kernel(int n, cg_dstate<T> *st, double tol, int max_iter, const T * __restrict__ b,
+                                                               const T * __restrict__ q, T *r, T *p, void *partials_v, unsigned int *ticket){
+    __shared__ double red[32];
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
+        T ri = hsub(b[i], q[i]);
+        r[i] = ri; p[i] = ri;
+        acc += (double) habs2(ri);
+    }
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double bs = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0){
+            st->rr = from_real<T>((real_t<T>) rr);      // all-reduced next, then dcg_begin_kernel turns it into zr[0]
+            st->zr[0] = zero_of<T>(); st->zr[1] = zero_of<T>(); st->pAp = one_of<T>();
+            st->rnorm = 0; st->tol = tol; st->iterations = 1; st->max_iter = max_iter; st->done[0] = 0; st->done[1] = 0;
+        }
+    }
+}
+template<typename T> __global__ void dcg_begin_kernel(cg_dstate<T> *st){ st->zr[0] = st->rr; st->rnorm = sqrt((double) hreal(st->rr)); }
+
+template<typename T>
+__global__ void __launch_bounds__(DK_THREADS) dcg_update_kernel(int n, cg_dstate<T> *st, int parity, const T * __restrict__ p, const T * __restrict__ q,
+                                                                T *x, T *r, void *partials_v, unsigned int *ticket){
+    __shared__ double red[32];
+    if (st->done[parity]) return;
+    const T a = hdiv(st->zr[parity], st->pAp);
+    const T na = hneg(a);
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
+        x[i] = hfma(a, p[i], x[i]);
+        T ri = hfma(na, q[i], r[i]);
+        r[i] = ri;
+        acc += (double) habs2(ri);
+    }
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double b = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0) st->rr = from_real<T>((real_t<T>) rr);
+    }
+}
+// after the all-reduce of rr: stop test (every thread evaluates the same scalars), p = r + beta p, bookkeeping by one thread
+template<typename T>
+__global__ void __launch_bounds__(DK_THREADS) dcg_direction_kernel(int n, cg_dstate<T> *st, int parity, int it_now, const T * __restrict__ r, T *p,
+                                                                   cg_dhost *host){
+    if (st->done[parity]){
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
+        return;
+    }
+    const T rr = st->rr, zr = st->zr[parity];
+    const double nrm = sqrt((double) hreal(rr));
+    const int stop = (it_now >= st->max_iter) || (nrm < st->tol) || !(nrm == nrm);
+    if (!stop){
+        const T beta = hdiv(rr, zr);
+        const size_t stride = (size_t) gridDim.x * blockDim.x;
+        for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride)
+            p[i] = hfma(beta, p[i], r[i]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0){
+        st->zr[parity ^ 1] = rr;
+        st->done[parity ^ 1] = stop;
+        st->iterations = it_now;
+        st->rnorm = nrm;
+        if (host){ host->rnorm = nrm; host->iterations = it_now; __threadfence_system(); if (stop) host->done = 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static ncclDataType_t real_dtype(int dtype){ return (dtype == HB_F32 || dtype == HB_C32) ? ncclFloat32 : ncclFloat64; }
+static int reals_per_scalar(int dtype){ return (dtype == HB_C32 || dtype == HB_C64) ? 2 : 1; }
+static int dgrid(const hb_ctx *ctx, long long n, int per_block){
+    long long need = (n + per_block - 1) / per_block, cap = (long long) ctx->num_sms * 4;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+extern "C" {
+
+int hb_dist_unique_id(void *id128){
+    HB_ARG(id128, "null");
+    int rc = load_nccl(); if (rc != HB_OK) return rc;
+    ncclUniqueId id;
+    HB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, HB_NCCL_ID_BYTES);
+    return HB_OK;
+}
+
+int hb_dist_create(hb_ctx *ctx, int rank, int world, const void *id128, hb_dist **out){
+    HB_ARG(ctx && id128 && out, "null");
+    HB_ARG(world >= 1 && rank >= 0 && rank < world, "rank/world");
+    int rc = load_nccl(); if (rc != HB_OK) return rc;
+    HB_CUDA(cudaSetDevice(ctx->device));
+    hb_dist *d = new hb_dist();
+    d->ctx = ctx; d->rank = rank; d->world = world;
+    ncclUniqueId id;
+    memcpy(&id, id128, HB_NCCL_ID_BYTES);
+    ncclResult_t r = g_nccl.CommInitRank(&d->comm, world, id, rank);
+    if (r != ncclSuccess){ delete d; return nccl_fail(r, "ncclCommInitRank"); }
+    *out = d;
+    return HB_OK;
+}
+
+int hb_dist_destroy(hb_dist *d){
+    if (!d) return HB_OK;
+    if (d->sendbuf) cudaFree(d->sendbuf);
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    delete d;
+    return HB_OK;
+}
+
+int hb_dist_info(const hb_dist *d, int *rank, int *world){
+    HB_ARG(d, "dist is null");
+    if (rank) *rank = d->rank;
+    if (world) *world = d->world;
+    return HB_OK;
+}
+
+int hb_dist_set_plan(hb_dist *d, int n_owned, int n_ghost, int nneigh, const int *neigh, const int *send_count, const int *recv_count,
+                     const int *send_idx_dev){
+    HB_ARG(d, "dist is null");
+    HB_ARG(n_owned >= 0 && n_ghost >= 0 && nneigh >= 0, "negative size");
+    HB_ARG(nneigh == 0 || (neigh && send_count && recv_count), "null plan arrays");
+    d->n_owned = n_owned; d->n_ghost = n_ghost;
+    d->neigh.assign(neigh, neigh + nneigh);
+    d->send_count.assign(send_count, send_count + nneigh);
+    d->recv_count.assign(recv_count, recv_count + nneigh);
+    long long st = 0, rt = 0;
+    for (int k = 0; k < nneigh; k++){
+        HB_ARG(neigh[k] >= 0 && neigh[k] < d->world && neigh[k] != d->rank, "neighbour rank");
+        st += send_count[k]; rt += recv_count[k];
+    }
+    HB_ARG(rt == n_ghost, "recv counts do not add up to n_ghost");
+    HB_ARG(st == 0 || send_idx_dev, "send_idx is null");
+    d->send_total = (int) st;
+    d->send_idx = send_idx_dev;
+    const size_t need = (size_t) st * 16;
+    if (need > d->sendbuf_bytes){
+        if (d->sendbuf) HB_CUDA(cudaFree(d->sendbuf));
+        HB_CUDA(cudaMalloc(&d->sendbuf, need));
+        d->sendbuf_bytes = need;
+    }
+    return HB_OK;
+}
+
+int hb_dist_halo_exchange(hb_dist *d, int dtype, void *x_ext){
+    HB_ARG(d && (x_ext || d->n_owned + d->n_ghost == 0), "null");
+    hb_ctx *ctx = d->ctx;
+    if (d->neigh.empty()) return HB_OK;
+    const size_t es = hb_dtype_size(dtype);
+    if (d->send_total > 0){
+        int grid = dgrid(ctx, d->send_total, 256);
+        HB_DISPATCH(dtype, (pack_kernel<T><<<grid, 256, 0, ctx->stream>>>(d->send_total, d->send_idx, (const T*) x_ext, (T*) d->sendbuf)));
+        HB_LAUNCH_CHECK(ctx);
+    }
+    const int rps = reals_per_scalar(dtype);
+    const ncclDataType_t nt = real_dtype(dtype);
+    HB_NCCL(g_nccl.GroupStart());
+    size_t soff = 0, roff = 0;
+    for (size_t k = 0; k < d->neigh.size(); k++){
+        if (d->send_count[k] > 0)
+            HB_NCCL(g_nccl.Send((char*) d->sendbuf + soff * es, (size_t) d->send_count[k] * rps, nt, d->neigh[k], d->comm, ctx->stream));
+        if (d->recv_count[k] > 0)
+            HB_NCCL(g_nccl.Recv((char*) x_ext + ((size_t) d->n_owned + roff) * es, (size_t) d->recv_count[k] * rps, nt, d->neigh[k], d->comm, ctx->stream));
+        soff += d->send_count[k]; roff += d->recv_count[k];
+    }
+    HB_NCCL(g_nccl.GroupEnd());
+    return HB_OK;
+}
+
+int hb_dist_allreduce_sum(hb_dist *d, int dtype, void *dev_scalars, int count){
+    HB_ARG(d && dev_scalars && count >= 0, "null");
+    if (d->world == 1 || count == 0) return HB_OK;
+    HB_NCCL(g_nccl.AllReduce(dev_scalars, dev_scalars, (size_t) count * reals_per_scalar(dtype), real_dtype(dtype), ncclSum, d->comm, d->ctx->stream));
+    return HB_OK;
+}
+
+int hb_dist_spmv(hb_dist *d, const hb_csr *A, void *x_ext, void *y){
+    HB_ARG(d && A, "null");
+    HB_ARG(A->rows == d->n_owned && A->cols == d->n_owned + d->n_ghost, "matrix shape does not match the exchange plan");
+    int rc = hb_dist_halo_exchange(d, A->dtype, x_ext);
+    if (rc != HB_OK) return rc;
+    return hb_spmv_internal(d->ctx, A, x_ext, y, nullptr);
+}
+
+int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+    HB_ARG(d && A && b && x, "null");
+    HB_ARG(A->rows == d->n_owned && A->cols == d->n_owned + d->n_ghost, "matrix shape does not match the exchange plan");
+    hb_ctx *ctx = d->ctx;
+    const int n = d->n_owned, dtype = A->dtype;
+    const size_t es = hb_dtype_size(dtype);
+    const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256, ext_bytes = ((es * ((size_t) n + d->n_ghost) + 255) / 256) * 256;
+    void *arena = nullptr;
+    int rc;
+    // r | Ap | p_ext | state
+    if ((rc = hb_ctx_workspace(ctx, 2 * vec_bytes + ext_bytes + 256, &arena)) != HB_OK) return rc;
+    char *base = (char*) arena;
+    void *r = base, *Ap = base + vec_bytes, *p = base + 2 * vec_bytes, *state = base + 2 * vec_bytes + ext_bytes;
+    cg_dhost *hstat = reinterpret_cast<cg_dhost*>(reinterpret_cast<char*>(ctx->hscalars) + 512);
+    void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 512;
+    hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
+    const int grid = dgrid(ctx, n, DK_THREADS * 4);
+
+    // p_ext <- x0 (owned), ghosts exchanged; Ap = A x0; r = b - Ap; p = r; zr = all-reduced <r,r>
+    HB_CUDA(cudaMemcpyAsync(p, x, es * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = hb_dist_halo_exchange(d, dtype, p)) != HB_OK) return rc;
+    if ((rc = hb_spmv_internal(ctx, A, p, Ap, nullptr)) != HB_OK) return rc;
+    HB_DISPATCH(dtype, {
+        cg_dstate<T> *st = (cg_dstate<T>*) state;
+        dcg_setup_kernel<T><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, tol, max_iter, (const T*) b, (const T*) Ap, (T*) r, (T*) p, ctx->partials, ctx->tickets + 6);
+        HB_LAUNCH_CHECK(ctx);
+        if ((rc = hb_dist_allreduce_sum(d, dtype, &st->rr, 1)) != HB_OK) return rc;
+        dcg_begin_kernel<T><<<1, 1, 0, ctx->stream>>>(st);
+        HB_LAUNCH_CHECK(ctx);
+    });
+
+    cudaEvent_t ev[2];
+    HB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    const int batch = 4;
+    long long it = 0;
+    int status = HB_OK;
+    for (long long bidx = 0; status == HB_OK; bidx++){
+        for (int j = 0; j < batch && status == HB_OK; j++, it++){
+            const int parity = (int) (it & 1);
+            HB_DISPATCH(dtype, {
+                cg_dstate<T> *st = (cg_dstate<T>*) state;
+                // every rank runs the collectives of every enqueued iteration, converged or not (the kernels around them
+                // are skipped by the done flag); all ranks see the same flag, so the call sequences stay matched
+                if ((status = hb_dist_halo_exchange(d, dtype, p)) != HB_OK) break;
+                if ((status = hb_spmv_dot_internal(ctx, A, p, Ap, &st->pAp, &st->done[parity])) != HB_OK) break;
+                if ((status = hb_dist_allreduce_sum(d, dtype, &st->pAp, 1)) != HB_OK) break;
+                dcg_update_kernel<T><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, (const T*) p, (const T*) Ap, (T*) x, (T*) r, ctx->partials, ctx->tickets + 6);
+                ctx->launches++;
+                if ((status = hb_dist_allreduce_sum(d, dtype, &st->rr, 1)) != HB_OK) break;
+                dcg_direction_kernel<T><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, (int) (it + 2), (const T*) r, (T*) p, (cg_dhost*) hstat_dev);
+                ctx->launches++;
+            });
+        }
+        if (status != HB_OK) break;
+        if (cudaEventRecord(ev[bidx & 1], ctx->stream) != cudaSuccess){ status = hb_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
+        if (bidx > 0){
+            if (cudaEventSynchronize(ev[(bidx - 1) & 1]) != cudaSuccess){ status = hb_cuda_fail(cudaGetLastError(), "cudaEventSynchronize"); break; }
+            if (hstat->done) break;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (status != HB_OK) return status;
+    if (e != cudaSuccess) return hb_cuda_fail(e, "cudaStreamSynchronize");
+    if (iters) *iters = hstat->iterations;
+    if (res) *res = hstat->rnorm;
+    return HB_OK;
+}
+
+}

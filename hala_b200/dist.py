@@ -1,0 +1,171 @@
+"""Multi-GPU host layer: one process per GPU, torch.distributed for the rendezvous, libhalab200's own NCCL communicator for
+the data path (halo exchange + scalar all-reduce inside hb_dist_cg).  Used by bench.py --gpus N and the multi-rank tests."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import capi, partition
+from .capi import lib, check
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_pi, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_void_p)
+DIST_SIGNATURES = {
+    "hb_dist_unique_id": (_i, [_vp]),
+    "hb_dist_create": (_i, [_vp, _i, _i, _vp, _pvp]),
+    "hb_dist_destroy": (_i, [_vp]),
+    "hb_dist_info": (_i, [_vp, _pi, _pi]),
+    "hb_dist_set_plan": (_i, [_vp, _i, _i, _i, _pi, _pi, _pi, _vp]),
+    "hb_dist_halo_exchange": (_i, [_vp, _i, _vp]),
+    "hb_dist_allreduce_sum": (_i, [_vp, _i, _vp, _i]),
+    "hb_dist_cg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi, C.POINTER(_d)]),
+    "hb_dist_spmv": (_i, [_vp, _vp, _vp, _vp]),
+}
+for _name, (_res, _args) in DIST_SIGNATURES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class Communicator:
+    """hb_dist handle of this rank; the NCCL unique id travels over torch.distributed (any backend)."""
+
+    def __init__(self, engine, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.engine, self.rank, self.world = engine, rank, world
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(lib.hb_dist_unique_id(buf), "hb_dist_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            ident = ident.cuda()
+        dist.broadcast(ident, src=0, group=group)
+        raw = bytes(ident.cpu().tolist())
+        self.h = C.c_void_p()
+        check(lib.hb_dist_create(engine.ctx, rank, world, raw, C.byref(self.h)), "hb_dist_create")
+        self._keep = None
+
+    def set_plan(self, n_owned, n_ghost, plan):
+        k = len(plan["neigh"])
+        arr = lambda v: (C.c_int * max(k, 1))(*v) if k else (C.c_int * 1)()
+        self._keep = plan["send_idx"]
+        check(lib.hb_dist_set_plan(self.h, n_owned, n_ghost, k, arr(plan["neigh"]), arr(plan["send_count"]), arr(plan["recv_count"]),
+                                   C.c_void_p(plan["send_idx"].data_ptr() if plan["send_idx"].numel() else 0)), "hb_dist_set_plan")
+
+    def cg(self, csr, b_ptr, x_ptr, tol, max_iter):
+        it, res = C.c_int(0), C.c_double(0)
+        check(lib.hb_dist_cg(self.h, csr.h, b_ptr, x_ptr, float(tol), int(max_iter), C.byref(it), C.byref(res)), "hb_dist_cg")
+        return it.value, res.value
+
+    def spmv(self, csr, x_ext_ptr, y_ptr):
+        check(lib.hb_dist_spmv(self.h, csr.h, x_ext_ptr, y_ptr), "hb_dist_spmv")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.hb_dist_destroy(self.h)
+        except Exception:
+            pass
+
+
+def build_local_problem(engine, comm, name, n, device, group=None):
+    """This rank's row slab of the n^3 stencil `name`, columns renumbered to [owned | ghosts], exchange plan installed."""
+    import torch
+    from . import devgen
+    import hala_b200 as hb
+    N = n ** (2 if name == "lap2d" else 3)
+    lo, hi = partition.block_range(N, comm.world, comm.rank)
+    tp, ti, tv = devgen.stencil_slab(name, n, lo, hi, device=device)
+    ti_local, ghosts = partition.build_ghost_map(ti, lo, hi)
+    del ti
+    plan = partition.exchange_plan(ghosts, N, comm.world, comm.rank, lo, group=group, device=device)
+    n_owned, n_ghost = hi - lo, int(ghosts.numel())
+    comm.set_plan(n_owned, n_ghost, plan)
+    gp, gi, gv = (devgen.torch_view(engine, t) for t in (tp, ti_local, tv))
+    A = hb.gpu_sparse_matrix(engine, n_owned, n_owned + n_ghost, ti_local.numel(), gp, gi, gv)
+    return {"A": A, "N": N, "lo": lo, "hi": hi, "n_owned": n_owned, "n_ghost": n_ghost, "nnz_local": ti_local.numel(),
+            "tensors": (tp, ti_local, tv), "plan": plan}
+
+
+def run_bench(args, slab, ClockSampler, measured_peak):
+    """bench.py --gpus N (N > 1), launched by torch.distributed.run: strong scaling of CG on the n^3 7-point Laplacian."""
+    import torch
+    import torch.distributed as dist
+    import hala_b200 as hb
+    from . import matgen as mg
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    e = hb.gpu_engine(local)
+    comm = Communicator(e, rank, world)
+    peak, peak_src = measured_peak()
+    n = args.grid
+    prob = build_local_problem(e, comm, "lap3d7", n, dev)
+    N, n_owned = prob["N"], prob["n_owned"]
+    nnz_total = torch.tensor([prob["nnz_local"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(nnz_total)
+    nnz = int(nnz_total.item())
+    b = torch.full((n_owned,), 1.0 / np.sqrt(N), dtype=torch.float64, device=dev)
+    x = torch.zeros(n_owned, dtype=torch.float64, device=dev)
+
+    def solve(iters):
+        x.zero_()
+        return comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), 0.0, iters + 1)
+
+    solve(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = e.launch_count()
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e.timer_start()
+        it, res = solve(args.steps)
+        ms = e.timer_stop()
+        torch.cuda.synchronize()
+        dist.barrier()
+    launches = e.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    its = args.steps / ms * 1e3
+    Bcg = mg.cg_iter_bytes(N, nnz, 8)
+
+    # dominant kernel alone on this rank's slab: halo-free SpMV+dot launches, CUDA events, max over ranks
+    p_ext = torch.rand(n_owned + prob["n_ghost"], dtype=torch.float64, device=dev)
+    q = torch.empty(n_owned, dtype=torch.float64, device=dev)
+    slot = torch.zeros(4, dtype=torch.float64, device=dev)
+    args_k = (e.ctx, prob["A"].h, C.c_void_p(p_ext.data_ptr()), C.c_void_p(q.data_ptr()), C.c_void_p(slot.data_ptr()))
+    for _ in range(3):
+        check(lib.hb_spmv_dot(*args_k))
+    e.timer_start()
+    for _ in range(30):
+        check(lib.hb_spmv_dot(*args_k))
+    kms = torch.tensor([e.timer_stop() / 30], dtype=torch.float64, device=dev)
+    dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    kms = float(kms.item())
+    Bk = mg.spmv_bytes(n_owned, prob["nnz_local"], 8)
+    halo = torch.tensor([prob["n_ghost"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": "cg_iters_per_s", "value": its, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"lap3d7-{n} fp64 unpreconditioned CG, b=1/sqrt(N), x0=0 (BASELINE configs[2])", "rows": N, "nnz": nnz,
+                           "parallelism": f"{world} ranks, 1-D row blocks, ghost halo (ncclSend/Recv) + 2 scalar all-reduces per iteration",
+                           "l2": "inputs larger than L2; no flush", "step": "one CG iteration", "max_ghosts_per_rank": int(halo.item())},
+                "gbs": Bcg * its / 1e9, "frac_of_measured_peak": Bcg * its / 1e9 / (peak * world), "algorithmic_bytes_per_step": Bcg, "final_residual": res,
+                "roofline": {"bound": "hbm", "kernel": "spmv_pipe_kernel<double,...,DOT> on one rank's slab", "achieved": Bk / kms / 1e6, "peak": peak,
+                             "unit": "GB/s", "frac": Bk / kms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": Bk, "us_per_launch": kms * 1e3, "share_of_step": kms / (ms / args.steps),
+                             "how": "CUDA events around 30 back-to-back launches per rank, max over ranks"},
+                "cpu_baseline": None,
+                "e2e": None, "gpu_launches": launches, "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    del comm
+    dist.destroy_process_group()

@@ -1,0 +1,49 @@
+/* halab200_dist.h — multi-GPU extension of the C ABI (one process per GPU, NCCL over NVLink/NVSwitch).
+ *
+ * The reference has no multi-device path at all (one gpu_engine == one device id, gpu/hala_gpu_engine.hpp:55,60; its tests
+ * only loop over devices, tests/solvers_tests.cpp:58-68), so nothing here replaces a reference interface: these entry
+ * points are what BASELINE.json's north_star adds — 1-D row-block partition, ghost-entry halo exchange, scalar all-reduce.
+ * The ghost maps themselves are built by the host layer (hala_b200/partition.py) and handed over with hb_dist_set_plan.
+ * NCCL is resolved at run time (dlopen of libnccl.so.2), so libhalab200.so has no hard dependency on it.
+ */
+#ifndef HALAB200_DIST_H
+#define HALAB200_DIST_H
+#include "halab200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_dist hb_dist;
+enum { HB_NCCL_ID_BYTES = 128 };
+
+/* rank 0 creates the id, the launcher broadcasts the 128 bytes (torch.distributed / MPI / a file), every rank calls create */
+int hb_dist_unique_id(void *id128);
+int hb_dist_create(hb_ctx *ctx, int rank, int world, const void *id128, hb_dist **dist);
+int hb_dist_destroy(hb_dist *dist);
+int hb_dist_info(const hb_dist *dist, int *rank, int *world);
+
+/* Exchange plan of this rank.  n_owned rows/columns are owned; ghost columns are numbered n_owned .. n_owned + n_ghost - 1
+ * in the order they are received: neighbour 0's block first, then neighbour 1's, ...
+ *   neigh[k]            rank of neighbour k (0 <= k < nneigh), ascending
+ *   send_count[k]       how many owned entries neighbour k needs;  send_idx (DEVICE, concatenated) = their local indices
+ *   recv_count[k]       how many ghost entries come from neighbour k (sum == n_ghost)                                        */
+int hb_dist_set_plan(hb_dist *dist, int n_owned, int n_ghost, int nneigh, const int *neigh,
+                     const int *send_count, const int *recv_count, const int *send_idx_dev);
+
+/* x_ext = [x_owned | ghosts]: packs the requested owned entries, grouped ncclSend/ncclRecv, ghosts land in x_ext + n_owned */
+int hb_dist_halo_exchange(hb_dist *dist, int dtype, void *x_ext);
+/* in-place sum over ranks of `count` scalars of `dtype` that live on the device */
+int hb_dist_allreduce_sum(hb_dist *dist, int dtype, void *dev_scalars, int count);
+
+/* Row-partitioned CG.  csr = local rows with columns renumbered to [owned | ghosts] (cols == n_owned + n_ghost);
+ * b, x = owned parts.  Same recurrence, counter and stop test as hb_cg; per iteration: halo exchange of p, SpMV fused with
+ * the local <p,Ap>, all-reduce, fused update + local ||r||^2, all-reduce, direction update.  All ranks return the same
+ * iteration count and residual.                                                                                            */
+int hb_dist_cg(hb_dist *dist, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, int *iters, double *res);
+/* y_owned = A_local * [x_owned | ghosts(x)]  (one halo exchange + one SpMV); x_ext must have room for the ghosts */
+int hb_dist_spmv(hb_dist *dist, const hb_csr *csr, void *x_ext, void *y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

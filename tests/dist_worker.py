@@ -1,0 +1,64 @@
+"""Multi-rank GPU worker (launched by torch.distributed.run from tests/test_gpu_dist.py): row-partitioned SpMV and CG on every
+rank against the single-GPU path and the CPU oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import hala_b200 as hb
+    from hala_b200 import matgen as mg, dist as hbdist
+    from oracle import binding
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    e = hb.gpu_engine(local)
+    comm = hbdist.Communicator(e, rank, world)
+    orc = binding.oracle()
+    for name, n, tol in (("lap3d7", 40, 1e-8), ("lap3d27", 24, 1e-8), ("lap2d", 200, 1e-8)):
+        prob = hbdist.build_local_problem(e, comm, name, n, dev)
+        N, lo, hi, n_owned, n_ghost = prob["N"], prob["lo"], prob["hi"], prob["n_owned"], prob["n_ghost"]
+        p, i, v = mg.GENERATORS[name](n)
+        # --- SpMV: P-way assembled y == oracle y (per-entry 1e-13)
+        xg = mg.probe_x(N)
+        x_ext = torch.zeros(n_owned + n_ghost, dtype=torch.float64, device=dev)
+        x_ext[:n_owned] = torch.from_numpy(xg[lo:hi]).to(dev)
+        y = torch.empty(n_owned, dtype=torch.float64, device=dev)
+        comm.spmv(prob["A"], C.c_void_p(x_ext.data_ptr()), C.c_void_p(y.data_ptr()))
+        yref = orc.spmv(p, i, v, xg)[lo:hi]
+        scale = np.abs(v).max() * 27 * 1.0
+        assert np.max(np.abs(y.cpu().numpy() - yref)) <= 1e-13 * scale, (name, rank)
+        # --- CG: iteration count within +-2 of the oracle (== the reference), same count on all ranks, solution agrees
+        b = torch.full((n_owned,), 1.0 / np.sqrt(N), dtype=torch.float64, device=dev)
+        x = torch.zeros(n_owned, dtype=torch.float64, device=dev)
+        it, res = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tol, 10 ** 6)
+        xo, ito = orc.cg(p, i, v, mg.rhs(N), tol)
+        its = torch.tensor([it], device=dev)
+        lst = [torch.zeros_like(its) for _ in range(world)]
+        dist.all_gather(lst, its)
+        assert all(int(t.item()) == it for t in lst), "ranks disagree on the iteration count"
+        assert abs(it - ito) <= 2, (name, it, ito)
+        assert res < tol
+        assert np.max(np.abs(x.cpu().numpy() - xo[lo:hi])) < 1e-6, name
+        # --- fixed iteration budget: exactly max_iter operator applications
+        x.zero_()
+        it2, _ = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), 0.0, 11)
+        assert it2 == 11, it2
+        if rank == 0:
+            print(f"dist ok: {name}:{n} world={world} cg {it} its (oracle {ito}), ghosts {n_ghost}", flush=True)
+        del prob
+    dist.barrier()
+    del comm
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

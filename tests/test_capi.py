@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "halab200.h")).read()
+    text = open(os.path.join(ROOT, "include", "halab200.h")).read() + open(os.path.join(ROOT, "include", "halab200_dist.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", text)))
 
@@ -21,7 +21,8 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 35
     for n in names:
         assert hasattr(capi.lib, n), f"{n} declared in include/halab200.h but not exported"
-    assert sorted(capi.SIGNATURES) == names, "capi.SIGNATURES and include/halab200.h disagree"
+    from hala_b200 import dist as hbdist
+    assert sorted(list(capi.SIGNATURES) + list(hbdist.DIST_SIGNATURES)) == names, "ctypes tables and include/*.h disagree"
     assert b"sm_100a" in capi.lib.hb_version()
 
 
