@@ -495,7 +495,7 @@ int hb_spmv(hb_ctx *ctx, const hb_csr *A, char trans, const void *alpha, const v
 
 int hb_spmv_dot(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev){
     HB_ARG(ctx && A && dot_dev, "null");
-    HB_ARG(A->rows == A->cols, "hb_spmv_dot needs a square matrix");
+    HB_ARG(A->cols >= A->rows, "hb_spmv_dot needs cols >= rows (x[i] pairs with y[i]; extra columns are ghost entries)");
     if (A->rows == 0){ HB_CUDA(cudaMemsetAsync(dot_dev, 0, hb_dtype_size(A->dtype), ctx->stream)); return HB_OK; }
     return hb_spmv_dot_internal(ctx, A, x, y, dot_dev, nullptr);
 }
