@@ -153,7 +153,7 @@ def run_ours(args):
     for _ in range(5):
         A1.gemv("N", 1.0, gx1, 0.0, gy1)
     e.timer_start()
-    reps = 200
+    reps = args.spmv_reps
     for _ in range(reps):
         A1.gemv("N", 1.0, gx1, 0.0, gy1)
     ms1 = e.timer_stop() / reps
@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID, help="edge of the 7-point problem (default 512 = BASELINE configs[2])")
     ap.add_argument("--ref-planes", type=int, default=24, help="z-planes of the slab the CPU reference is timed on")
+    ap.add_argument("--spmv-reps", type=int, default=200, help="timed launches of the configs[1] SpMV (lower it under ncu)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -316,7 +316,8 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
-                                                            A->cta_rows[CFG], ctx->partials, ctx->tickets + 1, dot_out, skip);
+                                                            A->cta_rows[CFG], ctx->partials, ctx->tickets + 1, dot_out, skip,
+                                                            (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -425,7 +426,7 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     }
     // equal-nnz row partition tables for the streaming kernel (one per pipeline configuration)
     const char *cfg_env = getenv("HB_PIPE_CFG");
-    A->pipe_cfg = (cfg_env && cfg_env[0] == '1') ? 1 : 0;
+    A->pipe_cfg = cfg_env ? ((cfg_env[0] == '1') ? 1 : 0) : (pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype)) >= 4 ? 1 : 0);
     A->vec_aligned = A->vec_aligned && aligned16p(pntr);
     if (rows > 0 && nnz > 0 && A->vec_aligned){
         for (int c = 0; c < 2; c++){
