@@ -153,6 +153,9 @@ __device__ __forceinline__ double shfl_down(double v, int d){ return __shfl_down
 template<typename R> __device__ __forceinline__ cplx<R> shfl_down(cplx<R> v, int d){
     return {shfl_down(v.re, d), shfl_down(v.im, d)};
 }
+__device__ __forceinline__ float  shfl_from(float v, int src){ return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_from(double v, int src){ return __shfl_sync(0xffffffffu, v, src); }
+template<typename R> __device__ __forceinline__ cplx<R> shfl_from(cplx<R> v, int src){ return {shfl_from(v.re, src), shfl_from(v.im, src)}; }
 template<typename T> __device__ __forceinline__ T warp_sum(T v){
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = hadd(v, shfl_down(v, d));

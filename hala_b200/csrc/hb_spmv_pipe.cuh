@@ -22,6 +22,7 @@
 // ring capacity per stage = THREADS * pipe_slots<T>() non-zeros; entries per lane per batch = the same number
 template<typename T> __host__ __device__ constexpr int pipe_slots(){ return sizeof(T) == 16 ? 4 : 8; }
 static constexpr int PIPE_LONGROW = 2048;       // slow path: rows at least this long are reduced by the whole CTA
+static constexpr int PIPE_WARPROW = 96;         // rows at least this long are reduced by a whole warp instead of TPR lanes
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p){ return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count){
@@ -172,6 +173,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                 // accumulators), so one row of up to PIPE_UNR*TPR entries costs a single gather round trip
                 const int end = re - a0;
                 T sum2 = zero_of<T>();
+                const bool wlong = (re - rs) >= PIPE_WARPROW;      // long rows: by the whole warp below, not by TPR lanes
+                if (!wlong)
                 for (int base = rs + sub - a0; base < end; base += PIPE_UNR * TPR){
                     int c[PIPE_UNR]; T v[PIPE_UNR], xv[PIPE_UNR]; bool ok[PIPE_UNR];
                     #pragma unroll
@@ -198,10 +201,48 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                     }
                 }
                 sum = hadd(sum, sum2);
+                // warp-cooperative pass over this warp's long rows (heavy-tailed row lengths): 32 lanes stride over the row in
+                // shared memory, four entries per lane in flight, shuffle reduction; the owner lane (sub == 0) keeps the sum
+                unsigned todo = __ballot_sync(0xffffffffu, wlong && sub == 0);
+                while (todo){
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int ls = __shfl_sync(0xffffffffu, rs, src) - a0, le = __shfl_sync(0xffffffffu, re, src) - a0;
+                    T part = zero_of<T>(), part2 = zero_of<T>();
+                    int j = ls + (tid & 31);
+                    for (; j + 96 < le; j += 128){
+                        const int c0 = sc[j], c1 = sc[j + 32], c2 = sc[j + 64], c3 = sc[j + 96];
+                        const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
+                        part = hfma(sv[j], x0, part); part2 = hfma(sv[j + 32], x1, part2);
+                        part = hfma(sv[j + 64], x2, part); part2 = hfma(sv[j + 96], x3, part2);
+                    }
+                    for (; j < le; j += 32) part = hfma(sv[j], ld_ro(x + sc[j]), part);
+                    part = shfl_from(warp_sum(hadd(part, part2)), 0);      // warp_sum leaves the total in lane 0
+                    if ((tid & 31) == src) sum = part;
+                }
             }else{
-                // slice larger than a stage: straight from global memory; very long rows by the whole CTA
-                if (re - rs < PIPE_LONGROW)
+                // slice larger than a stage: straight from global memory — short rows by their TPR lanes, long rows by the whole
+                // warp, very long rows (>= PIPE_LONGROW) by the whole CTA
+                const bool wlong = (re - rs) >= PIPE_WARPROW;
+                if (!wlong)
                     for (int j = rs + sub; j < re; j += TPR) sum = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), sum);
+                unsigned todo = __ballot_sync(0xffffffffu, wlong && sub == 0 && (re - rs) < PIPE_LONGROW);
+                while (todo){
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int ls = __shfl_sync(0xffffffffu, rs, src), le = __shfl_sync(0xffffffffu, re, src);
+                    T part = zero_of<T>(), part2 = zero_of<T>();
+                    int j = ls + (tid & 31);
+                    for (; j + 96 < le; j += 128){
+                        const int c0 = __ldcs(indx + j), c1 = __ldcs(indx + j + 32), c2 = __ldcs(indx + j + 64), c3 = __ldcs(indx + j + 96);
+                        const T v0 = ld_stream(vals + j), v1 = ld_stream(vals + j + 32), v2 = ld_stream(vals + j + 64), v3 = ld_stream(vals + j + 96);
+                        const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
+                        part = hfma(v0, x0, part); part2 = hfma(v1, x1, part2); part = hfma(v2, x2, part); part2 = hfma(v3, x3, part2);
+                    }
+                    for (; j < le; j += 32) part = hfma(ld_stream(vals + j), ld_ro(x + __ldcs(indx + j)), part);
+                    part = shfl_from(warp_sum(hadd(part, part2)), 0);      // warp_sum leaves the total in lane 0
+                    if ((tid & 31) == src) sum = part;
+                }
                 const int rlast = min(r0 + ROWS, rows);
                 for (int r = r0; r < rlast; r++){
                     const int ls = sp[r - r0], le = sp[r - r0 + 1];
