@@ -59,6 +59,10 @@ struct hb_dist {
     size_t sendbuf_bytes = 0;
 };
 
+hb_ctx* hb_dist_context(hb_dist *d){ return d->ctx; }
+int hb_dist_owned(const hb_dist *d){ return d->n_owned; }
+int hb_dist_ghosts(const hb_dist *d){ return d->n_ghost; }
+
 // ------------------------------------------------------------------------------------------------ kernels
 template<typename T> __global__ void pack_kernel(int n, const int * __restrict__ idx, const T * __restrict__ x, T *out){
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];

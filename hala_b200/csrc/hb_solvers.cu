@@ -6,8 +6,13 @@
 //           classical Gram-Schmidt step, Givens QR of the Hessenberg matrix on the host (k+2 scalars cross PCIe per inner
 //           iteration, once), packed back-substitution and the basis combination.
 #include "hb_common.cuh"
+#include "../../include/halab200_dist.h"
 #include <vector>
 #include <cmath>
+
+hb_ctx* hb_dist_context(hb_dist *d);
+int hb_dist_owned(const hb_dist *d);
+int hb_dist_ghosts(const hb_dist *d);
 
 int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
 int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
@@ -92,18 +97,24 @@ template<typename T> void h_tpsv_unn(int n, const std::vector<T> &ap, std::vecto
 }
 
 template<typename T>
-int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, int max_outer, int restart, int cproj, int *iters, double *res){
+int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, double tol_d, int max_outer, int restart, int cproj, int *iters, double *res){
     using R = real_t<T>;
     const int n = A->rows;
     const R tol = (R) tol_d;
     int rc;
-    // workspace: t | W (n x restart, column-major) | h (restart + 2 scalars), from the context's cached arena
-    const size_t vec_bytes = ((sizeof(T) * (size_t) n + 255) / 256) * 256;
+    // workspace: t | W (column-major, restart columns) | x_ext | h (restart + 2 scalars), from the context's cached arena.
+    // Row-partitioned run (dist != null): every basis column carries room for the ghost entries behind its n owned rows, so
+    // the halo of w_j is exchanged in place right before the SpMV that reads it; dots and norms are all-reduced.
+    const int next = A->cols;                               // n owned + ghosts (== n on one GPU)
+    const size_t vec_bytes = ((sizeof(T) * (size_t) next + 255) / 256) * 256;
     void *arena = nullptr;
-    if ((rc = hb_ctx_workspace(ctx, vec_bytes * ((size_t) restart + 1) + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
+    if ((rc = hb_ctx_workspace(ctx, vec_bytes * ((size_t) restart + 2) + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
     T *t = (T*) arena, *W = (T*) ((char*) arena + vec_bytes);
-    T *hdev = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 1));
+    T *xext = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 1));
+    T *hdev = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 2));
     const size_t ldw = vec_bytes / sizeof(T);
+    auto halo = [&](T *v)->int{ return dist ? hb_dist_halo_exchange(dist, A->dtype, v) : HB_OK; };
+    auto allsum = [&](T *v, int count)->int{ return dist ? hb_dist_allreduce_sum(dist, A->dtype, v, count) : HB_OK; };
     T *hhost = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->hscalars) + 1024);   // pinned staging, (restart+2) scalars <= 3 KiB
     HB_ARG((size_t) (restart + 2) * sizeof(T) <= HB_SCALAR_BYTES - 1024, "restart too large for the pinned staging area (max 190)");
     const int saved_mode = ctx->pointer_mode;
@@ -121,9 +132,16 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
         H.clear(); S.clear(); C.clear(); Z.clear();
         // t = b - A x ; r = P^-1 t (identity) ; inner_res = ||r|| ; W[:,0] = r / ||r||
         HB_CUDA(cudaMemcpyAsync(t, b, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
-        if ((rc = hb_spmv(ctx, A, 'N', &mone, x, &one, t)) != HB_OK) return rc;
+        const T *xin = x;
+        if (dist){
+            HB_CUDA(cudaMemcpyAsync(xext, x, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+            if ((rc = halo(xext)) != HB_OK) return rc;
+            xin = xext;
+        }
+        if ((rc = hb_spmv(ctx, A, 'N', &mone, xin, &one, t)) != HB_OK) return rc;
         total++;
         if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, 0, t, 0, t, t, hdev, -1.0, nullptr)) != HB_OK) return rc;     // hdev[0] = ||t||^2
+        if ((rc = allsum(hdev, 1)) != HB_OK) return rc;
         if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev, W, nullptr)) != HB_OK) return rc;
         HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
         HB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -132,12 +150,15 @@ int gmres_typed(hb_ctx *ctx, const hb_csr *A, const T *b, T *x, double tol_d, in
 
         int inner = 0;
         while ((inner_res > tol) && (inner < restart)){
-            const T *wj = W + (size_t) inner * ldw;
+            T *wj = W + (size_t) inner * ldw;
+            if ((rc = halo(wj)) != HB_OK) return rc;
             if ((rc = hb_spmv_internal(ctx, A, wj, t, nullptr)) != HB_OK) return rc;                         // t = A w_j ; r = P^-1 t
             total++;
             const int k = inner + 1;
             if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, ldw, t, hdev, nullptr)) != HB_OK) return rc;
+            if ((rc = allsum(hdev, k)) != HB_OK) return rc;
             if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, ldw, hdev, t, hdev + k, -1.0, nullptr)) != HB_OK) return rc;
+            if ((rc = allsum(hdev + k, 1)) != HB_OK) return rc;
             HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T) * (size_t) (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
             HB_CUDA(cudaStreamSynchronize(ctx->stream));
             coeffs.assign(hhost, hhost + k);
@@ -229,7 +250,16 @@ int hb_gmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, i
     HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
     HB_ARG(restart >= 1, "restart must be positive");
     if (A->rows == 0){ if (iters) *iters = 0; if (res) *res = 0; return HB_OK; }
-    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
+    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, nullptr, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
+    return HB_OK;
+}
+
+int hb_dist_gmres(hb_dist *dist, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, int *iters, double *res){
+    HB_ARG(dist && A && b && x, "null");
+    HB_ARG(restart >= 1, "restart must be positive");
+    hb_ctx *ctx = hb_dist_context(dist);
+    HB_ARG(A->rows == hb_dist_owned(dist) && A->cols == hb_dist_owned(dist) + hb_dist_ghosts(dist), "matrix shape does not match the exchange plan");
+    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, dist, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
     return HB_OK;
 }
 

@@ -21,6 +21,7 @@ DIST_SIGNATURES = {
     "hb_dist_allreduce_sum": (_i, [_vp, _i, _vp, _i]),
     "hb_dist_cg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi, C.POINTER(_d)]),
     "hb_dist_spmv": (_i, [_vp, _vp, _vp, _vp]),
+    "hb_dist_gmres": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _pi, C.POINTER(_d)]),
 }
 for _name, (_res, _args) in DIST_SIGNATURES.items():
     _f = getattr(lib, _name)
@@ -58,6 +59,11 @@ class Communicator:
     def cg(self, csr, b_ptr, x_ptr, tol, max_iter):
         it, res = C.c_int(0), C.c_double(0)
         check(lib.hb_dist_cg(self.h, csr.h, b_ptr, x_ptr, float(tol), int(max_iter), C.byref(it), C.byref(res)), "hb_dist_cg")
+        return it.value, res.value
+
+    def gmres(self, csr, b_ptr, x_ptr, tol, max_outer, restart, cproj=0):
+        it, res = C.c_int(0), C.c_double(0)
+        check(lib.hb_dist_gmres(self.h, csr.h, b_ptr, x_ptr, float(tol), int(max_outer), int(restart), int(cproj), C.byref(it), C.byref(res)), "hb_dist_gmres")
         return it.value, res.value
 
     def spmv(self, csr, x_ext_ptr, y_ptr):

@@ -40,6 +40,10 @@ int hb_dist_allreduce_sum(hb_dist *dist, int dtype, void *dev_scalars, int count
  * the local <p,Ap>, all-reduce, fused update + local ||r||^2, all-reduce, direction update.  All ranks return the same
  * iteration count and residual.                                                                                            */
 int hb_dist_cg(hb_dist *dist, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, int *iters, double *res);
+/* Row-partitioned GMRES(m): hb_gmres with the halo of each basis vector exchanged in place before its SpMV, the k Gram-Schmidt
+ * coefficients and the norm all-reduced (k + 1 scalars per inner iteration), Givens/Hessenberg replicated on every host. */
+int hb_dist_gmres(hb_dist *dist, const hb_csr *csr, const void *b, void *x, double tol, int max_outer, int restart, int cproj,
+                  int *iters, double *res);
 /* y_owned = A_local * [x_owned | ghosts(x)]  (one halo exchange + one SpMV); x_ext must have room for the ghosts */
 int hb_dist_spmv(hb_dist *dist, const hb_csr *csr, void *x_ext, void *y);
 

@@ -55,6 +55,20 @@ def main():
         if rank == 0:
             print(f"dist ok: {name}:{n} world={world} cg {it} its (oracle {ito}), ghosts {n_ghost}", flush=True)
         del prob
+    # --- row-partitioned GMRES(20) on the nonsymmetric convection-diffusion matrix against the oracle
+    name, n, tol = "convdiff7", 20, 1e-8
+    prob = hbdist.build_local_problem(e, comm, name, n, dev)
+    N, lo, hi, n_owned = prob["N"], prob["lo"], prob["hi"], prob["n_owned"]
+    p, i, v = mg.GENERATORS[name](n)
+    b = torch.full((n_owned,), 1.0 / np.sqrt(N), dtype=torch.float64, device=dev)
+    x = torch.zeros(n_owned, dtype=torch.float64, device=dev)
+    it, res = comm.gmres(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tol, 10 ** 6, 20)
+    xo, ito = orc.gmres(p, i, v, mg.rhs(N), tol, 20)
+    assert abs(it - ito) <= 2, (it, ito)
+    assert np.max(np.abs(x.cpu().numpy() - xo[lo:hi])) < 1e-6
+    if rank == 0:
+        print(f"dist ok: gmres {name}:{n} world={world} {it} its (oracle {ito})", flush=True)
+    del prob
     dist.barrier()
     del comm
     dist.destroy_process_group()
