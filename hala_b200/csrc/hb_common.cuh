@@ -49,6 +49,7 @@ struct hb_csr {
     // equal-nnz row partition for the persistent streaming kernel (hb_spmv_pipe.cuh): one table per pipeline config
     int *cta_rows[2] = {nullptr, nullptr};
     int  pipe_grid[2] = {0, 0};
+    int  pipe_contiguous = 0;           // 1: contiguous equal-nnz pieces per CTA (cta_rows table); 0: round-robin tile sweep
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
 };
 

@@ -316,7 +316,7 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
-                                                            A->cta_rows[CFG], ctx->partials, ctx->tickets + 1, dot_out, skip,
+                                                            A->pipe_contiguous ? A->cta_rows[CFG] : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip,
                                                             (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
@@ -428,6 +428,10 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     const char *cfg_env = getenv("HB_PIPE_CFG");
     A->pipe_cfg = cfg_env ? ((cfg_env[0] == '1') ? 1 : 0) : (pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype)) >= 4 ? 1 : 0);
     A->vec_aligned = A->vec_aligned && aligned16p(pntr);
+    {   // tile-to-CTA map of the streaming kernel: round-robin sweep by default, contiguous equal-nnz pieces on request
+        const char *m = getenv("HB_PIPE_MAP");
+        A->pipe_contiguous = m ? (m[0] == 'c' ? 1 : 0) : -1;       // -1: decided below from the row-length statistics
+    }
     if (rows > 0 && nnz > 0 && A->vec_aligned){
         for (int c = 0; c < 2; c++){
             const int threads = c == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
@@ -445,6 +449,9 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     }
     HB_CUDA(cudaMemcpyAsync(&A->max_row_nnz, A->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // heavy-tailed row lengths: equal-nnz contiguous pieces balance better than the sweep (power-law matrix: 623 vs 674 us);
+    // regular matrices: the sweep keeps the gather window of x in L2/L1 (27-point: 117 vs 151 us, 512^3 7-point: -13 % DRAM traffic)
+    if (A->pipe_contiguous < 0) A->pipe_contiguous = ((double) A->max_row_nnz > 16.0 * (A->mean_row_nnz + 1.0)) ? 1 : 0;
     *out = A;
     return HB_OK;
 }
