@@ -30,6 +30,21 @@ GRID = 512          # configs[2]
 SPMV_GRID = 128     # configs[1]
 
 
+def ncu_traffic(tag):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/traffic_r*.json, written here by
+    scripts/ncu_summary.py from the .ncu-rep); None when the workload is not the profiled one."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")), reverse=True):
+        try:
+            with open(f) as fh:
+                d = json.load(fh)
+            if tag in d:
+                return d[tag]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -45,6 +60,14 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        """nvidia-smi needs a few hundred ms to start: enter the context before the warm-up, mark the timed window here"""
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -58,7 +81,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -71,7 +94,11 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.1)]
+        if not rows and self.rows:      # window shorter than one sampling period: take the sample closest to it
+            mid = 0.5 * ((self.t0 or self.rows[0][0]) + (self.t1 or self.rows[-1][0]))
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -179,13 +206,15 @@ def run_ours(args):
         check(lib.hb_cg(e.ctx, A.h, gb.ptr, gx.ptr, 0.0, iters + 1, C.byref(it), C.byref(res)), "hb_cg")
         return it.value - 1, res.value
 
-    solve(max(args.warmup, 3))
-    torch.cuda.synchronize()
-    l0 = e.launch_count()
     with ClockSampler(local) as clk:
+        solve(max(args.warmup, 3))
+        torch.cuda.synchronize()
+        l0 = e.launch_count()
+        clk.mark_begin()
         e.timer_start()
         done, res = solve(args.steps)
         ms = e.timer_stop()
+        clk.mark_end()
     launches = e.launch_count() - l0
     assert done == args.steps, (done, args.steps)
     its = args.steps / ms * 1e3
@@ -204,7 +233,8 @@ def run_ours(args):
     kms = e.timer_stop() / kreps
     Bk = mg.spmv_bytes(N, nnz, 8)
     roof = {"bound": "hbm", "kernel": "spmv_pipe_kernel<double,...,DOT> (CSR SpMV fused with <p,Ap>)", "achieved": Bk / kms / 1e6, "peak": peak,
-            "unit": "GB/s", "frac": Bk / kms / 1e6 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": Bk,
+            "unit": "GB/s", "frac": Bk / kms / 1e6 / peak, "traffic": ncu_traffic(f"spmv_pipe_dot_lap3d7_{n}"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": Bk,
             "us_per_launch": kms * 1e3, "share_of_step": kms / (ms / args.steps),
             "how": "CUDA events around 30 back-to-back launches on the bench matrix, same process, right after the timed region"}
     del p_like, q

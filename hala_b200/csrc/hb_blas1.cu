@@ -8,10 +8,6 @@
 // block) adds the partials in fixed order, so results are bit-reproducible run to run.
 #include "hb_common.cuh"
 
-template<typename T> struct alignas(16) vec16 { static constexpr int N = 16 / sizeof(T); T v[N]; };
-
-static inline bool aligned16(const void *p){ return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 static constexpr int B1_THREADS = 256;
 static constexpr int B1_UNROLL  = 4;
 

@@ -127,6 +127,10 @@ template<> __host__ __device__ __forceinline__ double from_real<double>(double r
 template<> __host__ __device__ __forceinline__ cplx<float>  from_real<cplx<float>>(float r){ return {r, 0.f}; }
 template<> __host__ __device__ __forceinline__ cplx<double> from_real<cplx<double>>(double r){ return {r, 0.0}; }
 
+// 128-bit packets of T for the streaming kernels (unit stride, 16-byte aligned arrays)
+template<typename T> struct alignas(16) vec16 { static constexpr int N = 16 / sizeof(T); T v[N]; };
+static inline bool aligned16(const void *p){ return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // ----------------------------------------------------------------------------------------------------------------
 // loads: streaming (matrix data, touched once) vs cached read-only (x gather)
 // ----------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,29 @@
 
 static constexpr int KR_THREADS = 256;
 
+// ------------------------------------------------------------------------------------------------ streaming loop
+// Grid-stride sweep over n elements: when VEC, 128-bit packets with U independent packets per array in flight per thread
+// (all loads of a batch are issued before the first dependent FMA), then the scalar tail; otherwise element by element.
+//   load(u, packet index) / finish(u, packet index) work on packet slot u;  scalar(element index) handles one element.
+template<typename T, bool VEC, int U, typename FL, typename FF, typename FS>
+__device__ __forceinline__ void stream_sweep(size_t n, FL load, FF finish, FS scalar){
+    const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    size_t done = 0;
+    if (VEC){
+        const size_t nvec = n / vec16<T>::N;
+        size_t i = gtid;
+        for (; i + (U - 1) * stride < nvec; i += U * stride){
+            #pragma unroll
+            for (int u = 0; u < U; u++) load(u, i + u * stride);
+            #pragma unroll
+            for (int u = 0; u < U; u++) finish(u, i + u * stride);
+        }
+        for (; i < nvec; i += stride){ load(0, i); finish(0, i); }
+        done = nvec * vec16<T>::N;
+    }
+    for (size_t j = done + gtid; j < n; j += stride) scalar(j);
+}
+
 // ------------------------------------------------------------------------------------------------ CG state (device)
 // zr[2] is double-buffered by iteration parity so that no kernel both reads and writes the same scalar.
 template<typename T> struct cg_state {
@@ -15,29 +38,40 @@ template<typename T> struct cg_state {
     T pAp;              // <p, A p>
     double rnorm;       // ||r||_2 after the last update
     double tol;
-    int iterations;     // operator applications so far (reference counter, starts at 1)
+    int iterations;     // operator applications so far (reference counter, starts at 1); frozen once done
     int max_iter;
     int done;           // set by the update kernel when the reference's stop test fires
     int pad;
 };
 struct cg_host_status { volatile int done; volatile int iterations; volatile double rnorm; };
 
-// x += a p ; r -= a q ; rr = <r, r> ; then (last block) bookkeeping of solve_cg_core:  iterations, stop test, zr_next
-template<typename T>
-__global__ void __launch_bounds__(KR_THREADS) cg_update_kernel(int n, cg_state<T> *st, int parity, const T * __restrict__ p, const T * __restrict__ q,
-                                                               T *x, T *r, void *partials_v, unsigned int *ticket, cg_host_status *host){
+// Schedule of one iteration (10 vector passes instead of the 11 of the textbook split, 18 of the reference's BLAS-1 calls):
+//   spmv+dot   reads p, writes Ap                                  <p,Ap>
+//   update     r -= a Ap ; rr = <r,r>          reads r, Ap, writes r      (a = <r,z>/<p,Ap>, read from the device state)
+//   direction  x += a p ; p = r + b p          reads x, p, r, writes x, p (b = rr/<r,z>)
+// The x update rides in the direction kernel because that kernel streams p anyway: x leaves the update kernel, one pass saved.
+// Same arithmetic per element as solve_cg_core (hala_solvers_cg.hpp:135-148), so results are bit-identical to the 11-pass split.
+
+// r -= a q ; rr = <r, r> ; then (last block) bookkeeping of solve_cg_core: iterations, stop test, zr_next
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(KR_THREADS, 4) cg_update_kernel(int n, cg_state<T> *st, int parity, const T * __restrict__ q, T *r,
+                                                               void *partials_v, unsigned int *ticket, cg_host_status *host){
     __shared__ double red[32];
     if (st->done) return;
-    const T a = hdiv(st->zr[parity], st->pAp);
-    const T na = hneg(a);
+    const T na = hneg(hdiv(st->zr[parity], st->pAp));
     double acc = 0.0;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
-        x[i] = hfma(a, p[i], x[i]);
-        T ri = hfma(na, q[i], r[i]);
-        r[i] = ri;
-        acc += (double) habs2(ri);
-    }
+    constexpr int U = 4;
+    vec16<T> vr[U], vq[U];
+    vec16<T> *r4 = reinterpret_cast<vec16<T>*>(r);
+    const vec16<T> *q4 = reinterpret_cast<const vec16<T>*>(q);
+    stream_sweep<T, VEC, U>((size_t) n,
+        [&](int u, size_t i){ vr[u] = r4[i]; vq[u] = q4[i]; },
+        [&](int u, size_t i){
+            #pragma unroll
+            for (int k = 0; k < vec16<T>::N; k++){ vr[u].v[k] = hfma(na, vq[u].v[k], vr[u].v[k]); acc += (double) habs2(vr[u].v[k]); }
+            r4[i] = vr[u];
+        },
+        [&](size_t j){ T ri = hfma(na, q[j], r[j]); r[j] = ri; acc += (double) habs2(ri); });
     double *partials = reinterpret_cast<double*>(partials_v);
     double b = block_sum(acc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = b;
@@ -57,14 +91,37 @@ __global__ void __launch_bounds__(KR_THREADS) cg_update_kernel(int n, cg_state<T
         }
     }
 }
-// p = r + (zr_next / zr) p
-template<typename T>
-__global__ void __launch_bounds__(KR_THREADS) cg_direction_kernel(int n, const cg_state<T> *st, int parity, const T * __restrict__ r, T *p){
-    if (st->done) return;
+// x += a p ; p = r + (zr_next / zr) p.   it_now = the operator-application count the update kernel of THIS iteration produced:
+// when that update raised the stop flag the x update still has to happen (p is left alone); iterations enqueued after the
+// stop (st->iterations frozen at an earlier count) do nothing.
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(KR_THREADS, 4) cg_direction_kernel(int n, const cg_state<T> *st, int parity, int it_now, const T * __restrict__ r, T *p, T *x){
+    const bool stopped = st->done != 0;
+    if (stopped && st->iterations != it_now) return;
+    const T a = hdiv(st->zr[parity], st->pAp);
     const T beta = hdiv(st->zr[parity ^ 1], st->zr[parity]);
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride)
-        p[i] = hfma(beta, p[i], r[i]);
+    constexpr int U = 2;
+    vec16<T> vx[U], vp[U], vr[U];
+    vec16<T> *x4 = reinterpret_cast<vec16<T>*>(x), *p4 = reinterpret_cast<vec16<T>*>(p);
+    const vec16<T> *r4 = reinterpret_cast<const vec16<T>*>(r);
+    if (!stopped)
+        stream_sweep<T, VEC, U>((size_t) n,
+            [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = p4[i]; vr[u] = r4[i]; },
+            [&](int u, size_t i){
+                #pragma unroll
+                for (int k = 0; k < vec16<T>::N; k++){ vx[u].v[k] = hfma(a, vp[u].v[k], vx[u].v[k]); vp[u].v[k] = hfma(beta, vp[u].v[k], vr[u].v[k]); }
+                x4[i] = vx[u]; p4[i] = vp[u];
+            },
+            [&](size_t j){ const T pj = p[j]; x[j] = hfma(a, pj, x[j]); p[j] = hfma(beta, pj, r[j]); });
+    else
+        stream_sweep<T, VEC, U>((size_t) n,
+            [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = p4[i]; },
+            [&](int u, size_t i){
+                #pragma unroll
+                for (int k = 0; k < vec16<T>::N; k++) vx[u].v[k] = hfma(a, vp[u].v[k], vx[u].v[k]);
+                x4[i] = vx[u];
+            },
+            [&](size_t j){ x[j] = hfma(a, p[j], x[j]); });
 }
 
 // setup: r = b - q (q = A x0), p = r, zr[0] = <r,r>; state initialised by the last block
@@ -94,19 +151,28 @@ __global__ void __launch_bounds__(KR_THREADS) cg_setup_kernel(int n, cg_state<T>
 }
 
 // ------------------------------------------------------------------------------------------------ generic fused pieces (C ABI)
-template<typename T>
+template<typename T, bool VEC>
 __global__ void __launch_bounds__(KR_THREADS) axpy2_nrm2_kernel(int n, const T *a_dev, const T * __restrict__ p, const T * __restrict__ q,
                                                                 T *x, T *r, void *partials_v, unsigned int *ticket, T *rr_dev){
     __shared__ double red[32];
     const T a = *a_dev, na = hneg(a);
     double acc = 0.0;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride){
-        x[i] = hfma(a, p[i], x[i]);
-        T ri = hfma(na, q[i], r[i]);
-        r[i] = ri;
-        acc += (double) habs2(ri);
-    }
+    constexpr int U = 2;
+    vec16<T> vx[U], vp[U], vr[U], vq[U];
+    vec16<T> *x4 = reinterpret_cast<vec16<T>*>(x), *r4 = reinterpret_cast<vec16<T>*>(r);
+    const vec16<T> *p4 = reinterpret_cast<const vec16<T>*>(p), *q4 = reinterpret_cast<const vec16<T>*>(q);
+    stream_sweep<T, VEC, U>((size_t) n,
+        [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = p4[i]; vr[u] = r4[i]; vq[u] = q4[i]; },
+        [&](int u, size_t i){
+            #pragma unroll
+            for (int k = 0; k < vec16<T>::N; k++){
+                vx[u].v[k] = hfma(a, vp[u].v[k], vx[u].v[k]);
+                vr[u].v[k] = hfma(na, vq[u].v[k], vr[u].v[k]);
+                acc += (double) habs2(vr[u].v[k]);
+            }
+            x4[i] = vx[u]; r4[i] = vr[u];
+        },
+        [&](size_t j){ x[j] = hfma(a, p[j], x[j]); T ri = hfma(na, q[j], r[j]); r[j] = ri; acc += (double) habs2(ri); });
     double *partials = reinterpret_cast<double*>(partials_v);
     double b = block_sum(acc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = b;
@@ -115,12 +181,21 @@ __global__ void __launch_bounds__(KR_THREADS) axpy2_nrm2_kernel(int n, const T *
         if (threadIdx.x == 0) *rr_dev = from_real<T>((real_t<T>) rr);
     }
 }
-template<typename T>
+template<typename T, bool VEC>
 __global__ void __launch_bounds__(KR_THREADS) xpby_kernel(int n, const T * __restrict__ r, const T *b_dev, T *p){
     const T beta = *b_dev;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) n; i += stride)
-        p[i] = hfma(beta, p[i], r[i]);
+    constexpr int U = 4;
+    vec16<T> vp[U], vr[U];
+    vec16<T> *p4 = reinterpret_cast<vec16<T>*>(p);
+    const vec16<T> *r4 = reinterpret_cast<const vec16<T>*>(r);
+    stream_sweep<T, VEC, U>((size_t) n,
+        [&](int u, size_t i){ vp[u] = p4[i]; vr[u] = r4[i]; },
+        [&](int u, size_t i){
+            #pragma unroll
+            for (int k = 0; k < vec16<T>::N; k++) vp[u].v[k] = hfma(beta, vp[u].v[k], vr[u].v[k]);
+            p4[i] = vp[u];
+        },
+        [&](size_t j){ p[j] = hfma(beta, p[j], r[j]); });
 }
 
 // ------------------------------------------------------------------------------------------------ GMRES: multi-dot
@@ -329,16 +404,25 @@ int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol,
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
-int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *p, const void *q, void *x, void *r, void *host){
-    int grid = kr_grid(ctx, n, KR_THREADS * 4);
-    HB_DISPATCH(dtype, (cg_update_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) p, (const T*) q,
-                        (T*) x, (T*) r, ctx->partials, ctx->tickets + 4, (cg_host_status*) host)));
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host){
+    int grid = kr_grid(ctx, n, KR_THREADS * 8);
+    const bool vec = aligned16(q) && aligned16(r);
+    HB_DISPATCH(dtype, {
+        if (vec) cg_update_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) q, (T*) r,
+                                                                                  ctx->partials, ctx->tickets + 4, (cg_host_status*) host);
+        else     cg_update_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) q, (T*) r,
+                                                                                   ctx->partials, ctx->tickets + 4, (cg_host_status*) host);
+    });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
-int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, const void *r, void *p){
-    int grid = kr_grid(ctx, n, KR_THREADS * 4);
-    HB_DISPATCH(dtype, (cg_direction_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const cg_state<T>*) state, parity, (const T*) r, (T*) p)));
+int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, int it_now, const void *r, void *p, void *x){
+    int grid = kr_grid(ctx, n, KR_THREADS * 8);
+    const bool vec = aligned16(r) && aligned16(p) && aligned16(x);
+    HB_DISPATCH(dtype, {
+        if (vec) cg_direction_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const cg_state<T>*) state, parity, it_now, (const T*) r, (T*) p, (T*) x);
+        else     cg_direction_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const cg_state<T>*) state, parity, it_now, (const T*) r, (T*) p, (T*) x);
+    });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -379,8 +463,13 @@ int hb_axpy2_nrm2(hb_ctx *ctx, int dtype, int n, const void *a_dev, const void *
     HB_ARG(ctx && a_dev && rr_dev, "null");
     HB_ARG(n >= 0, "negative size");
     int grid = kr_grid(ctx, n, KR_THREADS * 4);
-    HB_DISPATCH(dtype, (axpy2_nrm2_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) a_dev, (const T*) p, (const T*) q, (T*) x, (T*) r,
-                        ctx->partials, ctx->tickets + 5, (T*) rr_dev)));
+    const bool vec = aligned16(p) && aligned16(q) && aligned16(x) && aligned16(r);
+    HB_DISPATCH(dtype, {
+        if (vec) axpy2_nrm2_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) a_dev, (const T*) p, (const T*) q, (T*) x, (T*) r,
+                                                                                   ctx->partials, ctx->tickets + 5, (T*) rr_dev);
+        else     axpy2_nrm2_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) a_dev, (const T*) p, (const T*) q, (T*) x, (T*) r,
+                                                                                    ctx->partials, ctx->tickets + 5, (T*) rr_dev);
+    });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -388,7 +477,11 @@ int hb_xpby(hb_ctx *ctx, int dtype, int n, const void *r, const void *b_dev, voi
     HB_ARG(ctx && b_dev, "null");
     if (n <= 0) return HB_OK;
     int grid = kr_grid(ctx, n, KR_THREADS * 4);
-    HB_DISPATCH(dtype, (xpby_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) r, (const T*) b_dev, (T*) p)));
+    const bool vec = aligned16(r) && aligned16(p);
+    HB_DISPATCH(dtype, {
+        if (vec) xpby_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) r, (const T*) b_dev, (T*) p);
+        else     xpby_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (const T*) r, (const T*) b_dev, (T*) p);
+    });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }

@@ -1,7 +1,7 @@
 // hb_solvers.cu — CG and GMRES with the iteration on the device.
 // hb_cg   : recurrence / counter / stop test of solve_cg_core (reference hex/solvers/hala_solvers_cg.hpp:92-156, wired as
-//           :181-227 with the identity preconditioner), three kernels per iteration (SpMV+<p,Ap>, x/r update+||r||^2,
-//           direction update), all scalars device-resident; the host only enqueues batches and polls a mapped flag.
+//           :181-227 with the identity preconditioner), three kernels per iteration (SpMV+<p,Ap>, r update+||r||^2,
+//           x and direction update), all scalars device-resident; the host only enqueues batches and polls a mapped flag.
 // hb_gmres: solve_gmres (hex/solvers/hala_solvers_gmres.hpp:127-230): SpMV, fused multi-dot + multi-axpy+norm as the
 //           classical Gram-Schmidt step, Givens QR of the Hessenberg matrix on the host (k+2 scalars cross PCIe per inner
 //           iteration, once), packed back-substitution and the basis combination.
@@ -21,8 +21,8 @@ int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const 
                            void *nrm2sq_dev, double scale, const int *skip);
 int hb_scale_copy_internal(hb_ctx *ctx, int dtype, long long rows, const void *r, const void *nrm2sq_dev, void *w_out, void *r_out);
 int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol, int max_iter, const void *b, const void *q, void *r, void *p, void *host);
-int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *p, const void *q, void *x, void *r, void *host);
-int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, const void *r, void *p);
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host);
+int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, int it_now, const void *r, void *p, void *x);
 size_t hb_cg_state_bytes(int dtype);
 size_t hb_cg_state_pap_offset(int dtype);
 size_t hb_cg_state_done_offset(int dtype);
@@ -230,8 +230,10 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
         for (int j = 0; j < batch; j++, it++){
             const int parity = (int) (it & 1);
             if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;               // Ap = A p ; <p,Ap>
-            if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, p, Ap, x, r, hstat_dev)) != HB_OK) return rc;
-            if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, r, p)) != HB_OK) return rc;
+            if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev)) != HB_OK) return rc;
+            // iteration `it` turns the operator-application counter into it + 2 (setup leaves it at 1)
+            const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
+            if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, it_now, r, p, x)) != HB_OK) return rc;
         }
         HB_CUDA(cudaEventRecord(evs.ev[bidx & 1], ctx->stream));
         if (bidx > 0){

@@ -122,17 +122,19 @@ def run_bench(args, slab, ClockSampler, measured_peak):
         x.zero_()
         return comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), 0.0, iters + 1)
 
-    solve(max(args.warmup, 3))
-    torch.cuda.synchronize()
-    dist.barrier()
-    l0 = e.launch_count()
     with ClockSampler(local) as clk:
+        solve(max(args.warmup, 3))
+        torch.cuda.synchronize()
+        dist.barrier()
+        l0 = e.launch_count()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        clk.mark_begin()
         e.timer_start()
         it, res = solve(args.steps)
         ms = e.timer_stop()
+        clk.mark_end()
         torch.cuda.synchronize()
         dist.barrier()
     launches = e.launch_count() - l0
