@@ -27,6 +27,10 @@ struct hb_ctx {
     // here a second solve of the same size allocates nothing).  Released by hb_ctx_trim / hb_ctx_destroy.
     void  *work = nullptr;
     size_t work_bytes = 0;
+    // set by the row-partitioned solvers around an SpMV+dot that is a step of a peer-transport iteration (hb_peer.cuh):
+    // the streaming kernel then waits for the halo flags of `peer_epoch` before it gathers and publishes its <x,y> partial
+    const void *peer_hook = nullptr;    // peer_view* in device memory
+    unsigned long long peer_epoch = 0;
 };
 int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr);
 
@@ -218,6 +222,30 @@ template<> __device__ __forceinline__ cplx<double> sum_partials<cplx<double>>(co
         acc = hadd(acc, cplx<double>{v.x, v.y});
     }
     return block_sum(acc, red);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// streaming loop
+// Grid-stride sweep over n elements: when VEC, 128-bit packets with U independent packets per array in flight per thread
+// (all loads of a batch are issued before the first dependent FMA), then the scalar tail; otherwise element by element.
+//   load(u, packet index) / finish(u, packet index) work on packet slot u;  scalar(element index) handles one element.
+template<typename T, bool VEC, int U, typename FL, typename FF, typename FS>
+__device__ __forceinline__ void stream_sweep(size_t n, FL load, FF finish, FS scalar){
+    const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    size_t done = 0;
+    if (VEC){
+        const size_t nvec = n / vec16<T>::N;
+        size_t i = gtid;
+        for (; i + (U - 1) * stride < nvec; i += U * stride){
+            #pragma unroll
+            for (int u = 0; u < U; u++) load(u, i + u * stride);
+            #pragma unroll
+            for (int u = 0; u < U; u++) finish(u, i + u * stride);
+        }
+        for (; i < nvec; i += stride){ load(0, i); finish(0, i); }
+        done = nvec * vec16<T>::N;
+    }
+    for (size_t j = done + gtid; j < n; j += stride) scalar(j);
 }
 
 // dtype dispatch on the host

@@ -1,13 +1,16 @@
 // hb_dist.cu — row-partitioned multi-GPU path: halo exchange, scalar all-reduce and the distributed CG iteration.
 // One process per GPU; NCCL (over NVLink 5 / NVSwitch) is loaded at run time.  New work: the reference is single-device.
 #include "hb_common.cuh"
+#include "hb_peer.cuh"
 #include "../../include/halab200_dist.h"
 #include <nccl.h>
+#include <cstdlib>
 #include <dlfcn.h>
 #include <vector>
 
 int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
 int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
+int hb_spmv_variant(const hb_csr *A);
 
 // ------------------------------------------------------------------------------------------------ NCCL, resolved lazily
 namespace {
@@ -18,6 +21,7 @@ struct nccl_api {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char*  (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -35,7 +39,7 @@ int load_nccl(){
     g_nccl.lib = h;
     #define HB_SYM(field, name) do { *(void**) (&g_nccl.field) = dlsym(h, name); if (!g_nccl.field){ hb_set_error(std::string("libnccl lacks ") + name); g_nccl.lib = nullptr; return HB_ERR_NCCL; } } while (0)
     HB_SYM(GetUniqueId, "ncclGetUniqueId"); HB_SYM(CommInitRank, "ncclCommInitRank"); HB_SYM(CommDestroy, "ncclCommDestroy");
-    HB_SYM(GetErrorString, "ncclGetErrorString"); HB_SYM(AllReduce, "ncclAllReduce"); HB_SYM(Send, "ncclSend"); HB_SYM(Recv, "ncclRecv");
+    HB_SYM(GetErrorString, "ncclGetErrorString"); HB_SYM(AllReduce, "ncclAllReduce"); HB_SYM(AllGather, "ncclAllGather"); HB_SYM(Send, "ncclSend"); HB_SYM(Recv, "ncclRecv");
     HB_SYM(GroupStart, "ncclGroupStart"); HB_SYM(GroupEnd, "ncclGroupEnd");
     #undef HB_SYM
     return HB_OK;
@@ -57,6 +61,15 @@ struct hb_dist {
     const int *send_idx = nullptr;      // device, caller-owned
     void *sendbuf = nullptr;            // device, send_total * 16 bytes
     size_t sendbuf_bytes = 0;
+    // ---- peer-memory transport (hb_peer.cuh): exchange buffer = mailbox | p buffer 0 | p buffer 1, mapped by every peer
+    int    peer_state = 0;              // 0 not tried for the current plan, 1 ready, -1 unavailable (NCCL path is used)
+    size_t peer_es = 0;                 // element size the p buffers were laid out for
+    void  *pbuf = nullptr;              // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
+    size_t pbuf_ext_bytes = 0;          // bytes of one p buffer
+    void  *peer_base[HB_MAX_PEERS] = {};// rank q's exchange buffer as mapped into this process (q == rank: pbuf)
+    peer_view *pv_dev = nullptr;
+    unsigned long long epoch = 0;       // global iteration number of the peer protocol; same on every rank
+    int    plan_version = 0;
 };
 
 hb_ctx* hb_dist_context(hb_dist *d){ return d->ctx; }
@@ -77,6 +90,7 @@ template<typename T> struct cg_dstate {
     double rnorm, tol;
     int iterations, max_iter;
     int done[2];
+    T pAp_local;        // peer transport: this rank's <p,Ap> partial as written by the SpMV+dot kernel
 };
 struct cg_dhost { volatile int done; volatile int iterations; volatile double rnorm; };
 
@@ -156,6 +170,121 @@ __global__ void __launch_bounds__(DK_THREADS) dcg_direction_kernel(int n, cg_dst
     }
 }
 
+// ------------------------------------------------------------------------------------------------ peer-transport CG kernels
+// One iteration g = three kernels and no collective call (protocol: hb_peer.cuh):
+//   SpMV+dot   waits for the halo flags of g, gathers from p[g&1] = [owned | ghosts], publishes its <p,Ap> partial (channel PAP)
+//   update     every block adds the W partials in rank order -> a = <r,z>/<p,Ap>; r -= a Ap; publishes its ||r||^2 partial (RR)
+//   direction  every block adds the W partials -> stop test, b; FIRST stores the entries its neighbours need of the new p into
+//              their ghost slots of buffer (g+1)&1 (recomputed from r and the old p, so no grid-wide dependency) and releases
+//              the flags of g+1, THEN sweeps x += a p_old, p_new = r + b p_old.  p ping-pongs between two buffers, which is
+//              what makes the early push legal and double-buffers the ghost slots for free.
+static constexpr int PK_MIN_GRID = HB_HALO_BLOCKS;
+
+__global__ void peer_halo_wait_kernel(const peer_view *pv, unsigned long long g, const int *skip){
+    if (skip && *skip) return;
+    peer_halo_wait(pv, g);
+}
+template<typename T> __global__ void peer_publish_kernel(const peer_view *pv, int channel, unsigned long long g, const T *value, const int *skip){
+    if (skip && *skip) return;
+    peer_publish<T>(pv, channel, g, *value);
+}
+// after the NCCL all-reduce of the setup's <r,r>: zr[0], ||r||, and the halo of the first direction p = r
+template<typename T>
+__global__ void __launch_bounds__(DK_THREADS) pcg_begin_kernel(cg_dstate<T> *st, const peer_view *pv, unsigned long long g,
+                                                               const int * __restrict__ send_idx, const T * __restrict__ p){
+    if (blockIdx.x == 0 && threadIdx.x == 0){ st->zr[0] = st->rr; st->rnorm = sqrt((double) hreal(st->rr)); }
+    peer_halo_push<T>(pv, g, [&](int j){ return p[send_idx[j]]; });
+}
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(DK_THREADS, 4) pcg_update_kernel(int n, cg_dstate<T> *st, int parity, unsigned long long g, const T * __restrict__ q,
+                                                                   T *r, void *partials_v, unsigned int *ticket, const peer_view *pv){
+    __shared__ double red[32];
+    __shared__ T s_pap;
+    __shared__ double s_rr;
+    if (st->done[parity]) return;
+    if (threadIdx.x < 32){
+        const T v = peer_wait_sum<T>(pv, HB_PEER_CH_PAP, g);
+        if (threadIdx.x == 0) s_pap = v;
+    }
+    __syncthreads();
+    const T pap = s_pap;
+    const T na = hneg(hdiv(st->zr[parity], pap));
+    double acc = 0.0;
+    constexpr int U = 4;
+    vec16<T> vr[U], vq[U];
+    vec16<T> *r4 = reinterpret_cast<vec16<T>*>(r);
+    const vec16<T> *q4 = reinterpret_cast<const vec16<T>*>(q);
+    stream_sweep<T, VEC, U>((size_t) n,
+        [&](int u, size_t i){ vr[u] = r4[i]; vq[u] = q4[i]; },
+        [&](int u, size_t i){
+            #pragma unroll
+            for (int k = 0; k < vec16<T>::N; k++){ vr[u].v[k] = hfma(na, vq[u].v[k], vr[u].v[k]); acc += (double) habs2(vr[u].v[k]); }
+            r4[i] = vr[u];
+        },
+        [&](size_t j){ T ri = hfma(na, q[j], r[j]); r[j] = ri; acc += (double) habs2(ri); });
+    double *partials = reinterpret_cast<double*>(partials_v);
+    double b = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_arrives(ticket)){
+        double rr = sum_partials<double>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0){ st->pAp = pap; s_rr = rr; }
+        __syncthreads();
+        if (threadIdx.x < 32) peer_publish<double>(pv, HB_PEER_CH_RR, g, s_rr);
+    }
+}
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(DK_THREADS, 4) pcg_direction_kernel(int n, cg_dstate<T> *st, int parity, unsigned long long g, int it_now,
+                                                                      const T * __restrict__ r, const T * __restrict__ p_old, T *p_new, T *x,
+                                                                      const peer_view *pv, const int * __restrict__ send_idx, cg_dhost *host){
+    __shared__ double s_rr;
+    if (st->done[parity]){
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
+        return;
+    }
+    if (threadIdx.x < 32){
+        const double v = peer_wait_sum<double>(pv, HB_PEER_CH_RR, g);
+        if (threadIdx.x == 0) s_rr = v;
+    }
+    __syncthreads();
+    const double rrd = s_rr;
+    const T rr = from_real<T>((real_t<T>) rrd), zr = st->zr[parity];
+    const double nrm = sqrt(rrd);
+    const int stop = (it_now >= st->max_iter) || (nrm < st->tol) || !(nrm == nrm);
+    const T a = hdiv(zr, st->pAp);
+    constexpr int U = 2;
+    vec16<T> vx[U], vp[U], vr[U];
+    vec16<T> *x4 = reinterpret_cast<vec16<T>*>(x), *pn4 = reinterpret_cast<vec16<T>*>(p_new);
+    const vec16<T> *r4 = reinterpret_cast<const vec16<T>*>(r), *po4 = reinterpret_cast<const vec16<T>*>(p_old);
+    if (!stop){
+        const T beta = hdiv(rr, zr);
+        peer_halo_push<T>(pv, g + 1, [&](int j){ const int i = send_idx[j]; return hfma(beta, p_old[i], r[i]); });
+        stream_sweep<T, VEC, U>((size_t) n,
+            [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = po4[i]; vr[u] = r4[i]; },
+            [&](int u, size_t i){
+                #pragma unroll
+                for (int k = 0; k < vec16<T>::N; k++){ vx[u].v[k] = hfma(a, vp[u].v[k], vx[u].v[k]); vp[u].v[k] = hfma(beta, vp[u].v[k], vr[u].v[k]); }
+                x4[i] = vx[u]; pn4[i] = vp[u];
+            },
+            [&](size_t j){ const T pj = p_old[j]; x[j] = hfma(a, pj, x[j]); p_new[j] = hfma(beta, pj, r[j]); });
+    }else{
+        stream_sweep<T, VEC, U>((size_t) n,
+            [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = po4[i]; },
+            [&](int u, size_t i){
+                #pragma unroll
+                for (int k = 0; k < vec16<T>::N; k++) vx[u].v[k] = hfma(a, vp[u].v[k], vx[u].v[k]);
+                x4[i] = vx[u];
+            },
+            [&](size_t j){ x[j] = hfma(a, p_old[j], x[j]); });
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0){
+        st->zr[parity ^ 1] = rr;
+        st->done[parity ^ 1] = stop;
+        st->iterations = it_now;
+        st->rnorm = nrm;
+        if (host){ host->rnorm = nrm; host->iterations = it_now; __threadfence_system(); if (stop) host->done = 1; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ helpers
 static ncclDataType_t real_dtype(int dtype){ return (dtype == HB_F32 || dtype == HB_C32) ? ncclFloat32 : ncclFloat64; }
 static int reals_per_scalar(int dtype){ return (dtype == HB_C32 || dtype == HB_C64) ? 2 : 1; }
@@ -163,6 +292,235 @@ static int dgrid(const hb_ctx *ctx, long long n, int per_block){
     long long need = (n + per_block - 1) / per_block, cap = (long long) ctx->num_sms * 4;
     if (need < 1) need = 1;
     return (int) (need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------------------ peer transport: setup
+namespace {
+struct peer_info {                              // what every rank tells every other one (all-gathered through NCCL)
+    cudaIpcMemHandle_t handle;                  // 64 B
+    unsigned long long ext_bytes;               // bytes of one p buffer on that rank
+    long long ok;                               // 0: that rank cannot take the peer path
+    long long ghost_base[HB_MAX_PEERS];         // element index in that rank's p buffers where entries coming from rank q land (-1: none)
+    char pad[256 - 64 - 16 - 8 * HB_MAX_PEERS];
+};
+static_assert(sizeof(peer_info) == 256, "peer_info layout");
+
+bool peer_env_enabled(){
+    const char *e = getenv("HB_DIST_PEER");
+    return !(e && e[0] == '0');
+}
+bool peer_env_fused_spmv(){
+    const char *e = getenv("HB_PEER_FUSED_SPMV");
+    return !(e && e[0] == '0');
+}
+// in-place minimum over ranks of one int (agreement on "does everybody have it")
+int agree_min(hb_dist *d, int *value){
+    int *dv = reinterpret_cast<int*>(d->ctx->dscalars);
+    HB_CUDA(cudaMemcpyAsync(dv, value, sizeof(int), cudaMemcpyHostToDevice, d->ctx->stream));
+    HB_NCCL(g_nccl.AllReduce(dv, dv, 1, ncclInt32, ncclMin, d->comm, d->ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(value, dv, sizeof(int), cudaMemcpyDeviceToHost, d->ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(d->ctx->stream));
+    return HB_OK;
+}
+void peer_release(hb_dist *d){
+    for (int q = 0; q < HB_MAX_PEERS; q++){
+        if (d->peer_base[q] && q != d->rank) cudaIpcCloseMemHandle(d->peer_base[q]);
+        d->peer_base[q] = nullptr;
+    }
+    if (d->pbuf){ cudaFree(d->pbuf); d->pbuf = nullptr; }
+    if (d->pv_dev){ cudaFree(d->pv_dev); d->pv_dev = nullptr; }
+    d->peer_es = 0; d->pbuf_ext_bytes = 0;
+    cudaGetLastError();
+}
+// Collective over all ranks.  HB_OK: the peer path is ready for element size `es`; HB_ERR_UNSUPPORTED: agreed by ALL ranks
+// that it is not available (the callers then take the NCCL path); anything else is an error.
+int peer_setup(hb_dist *d, size_t es){
+    if (d->peer_state == 1 && d->peer_es == es) return HB_OK;
+    if (d->peer_state == -1) return HB_ERR_UNSUPPORTED;
+    hb_ctx *ctx = d->ctx;
+    const int W = d->world;
+    int rc;
+    if (d->peer_state == 1){                    // laid out for another element size: everybody leaves the old buffers first
+        int one = 1;
+        if ((rc = agree_min(d, &one)) != HB_OK) return rc;
+        peer_release(d);
+        d->peer_state = 0;
+    }
+    const size_t ext_elems = (size_t) d->n_owned + d->n_ghost;
+    const size_t ext_bytes = ((es * ext_elems + 255) / 256) * 256;
+    peer_info mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = (d->neigh.size() <= (size_t) HB_MAX_NEIGH) ? 1 : 0;
+    mine.ext_bytes = ext_bytes;
+    for (int q = 0; q < HB_MAX_PEERS; q++) mine.ghost_base[q] = -1;
+    {
+        long long roff = 0;
+        for (size_t k = 0; k < d->neigh.size(); k++){
+            if (d->recv_count[k] > 0) mine.ghost_base[d->neigh[k]] = (long long) d->n_owned + roff;
+            roff += d->recv_count[k];
+        }
+    }
+    // whole 2 MiB pages: small cudaMalloc requests are carved out of a shared block, and an IPC handle exports the block
+    const size_t pbuf_bytes = ((HB_MAILBOX_BYTES + 2 * ext_bytes + (2u << 20) - 1) >> 21) << 21;
+    if (mine.ok){
+        if (cudaMalloc(&d->pbuf, pbuf_bytes) != cudaSuccess){ cudaGetLastError(); d->pbuf = nullptr; mine.ok = 0; }
+        else if (cudaMemsetAsync(d->pbuf, 0, pbuf_bytes, ctx->stream) != cudaSuccess
+                 || cudaIpcGetMemHandle(&mine.handle, d->pbuf) != cudaSuccess){ cudaGetLastError(); mine.ok = 0; }
+    }
+    // all-gather the 256-byte records
+    char *stage = nullptr;
+    HB_CUDA(cudaMalloc((void**) &stage, sizeof(peer_info) * (size_t) (W + 1)));
+    std::vector<peer_info> all((size_t) W);
+    cudaError_t ce = cudaMemcpyAsync(stage, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (ce == cudaSuccess) nr = g_nccl.AllGather(stage, stage + sizeof(peer_info), sizeof(peer_info), ncclChar, d->comm, ctx->stream);
+    if (ce == cudaSuccess && nr == ncclSuccess) ce = cudaMemcpyAsync(all.data(), stage + sizeof(peer_info), sizeof(peer_info) * (size_t) W, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess && nr == ncclSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (nr != ncclSuccess) return nccl_fail(nr, "ncclAllGather (peer setup)");
+    if (ce != cudaSuccess) return hb_cuda_fail(ce, "peer setup exchange");
+    int ok = 1;
+    for (int q = 0; q < W; q++) if (!all[q].ok) ok = 0;
+    // map the peers' buffers
+    if (ok){
+        d->peer_base[d->rank] = d->pbuf;
+        for (int q = 0; q < W && ok; q++){
+            if (q == d->rank) continue;
+            if (cudaIpcOpenMemHandle(&d->peer_base[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){
+                cudaGetLastError(); d->peer_base[q] = nullptr; ok = 0;
+            }
+        }
+    }
+    if ((rc = agree_min(d, &ok)) != HB_OK) return rc;
+    if (!ok){
+        peer_release(d);
+        d->peer_state = -1;
+        return HB_ERR_UNSUPPORTED;
+    }
+    peer_view pv;
+    memset(&pv, 0, sizeof(pv));
+    pv.rank = d->rank; pv.world = W; pv.nneigh = (int) d->neigh.size();
+    for (int q = 0; q < W; q++) pv.mail[q] = reinterpret_cast<peer_mailbox*>(d->peer_base[q]);
+    int soff = 0;
+    for (int k = 0; k < pv.nneigh; k++){
+        const int nq = d->neigh[k];
+        pv.neigh[k] = nq;
+        pv.recv_from[k] = d->recv_count[k] > 0;
+        pv.send_off[k] = soff;
+        soff += d->send_count[k];
+        for (int b = 0; b < 2; b++){
+            pv.ghost_dst[k][b] = nullptr;
+            if (d->send_count[k] > 0){
+                if (all[nq].ghost_base[d->rank] < 0){ hb_set_error("exchange plans of two neighbours disagree"); peer_release(d); return HB_ERR_ARG; }
+                pv.ghost_dst[k][b] = (char*) d->peer_base[nq] + HB_MAILBOX_BYTES + (size_t) b * all[nq].ext_bytes + (size_t) all[nq].ghost_base[d->rank] * es;
+            }
+        }
+    }
+    pv.send_off[pv.nneigh] = soff;
+    HB_CUDA(cudaMalloc((void**) &d->pv_dev, sizeof(peer_view)));
+    HB_CUDA(cudaMemcpy(d->pv_dev, &pv, sizeof(pv), cudaMemcpyHostToDevice));
+    d->peer_es = es; d->pbuf_ext_bytes = ext_bytes;
+    d->peer_state = 1;
+    return HB_OK;
+}
+
+// CG over the peer transport; see the kernel block above for the per-iteration protocol
+int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+    hb_ctx *ctx = d->ctx;
+    const int n = d->n_owned, dtype = A->dtype;
+    const size_t es = hb_dtype_size(dtype);
+    const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256;
+    void *arena = nullptr;
+    int rc;
+    if ((rc = hb_ctx_workspace(ctx, 2 * vec_bytes + 256, &arena)) != HB_OK) return rc;       // r | Ap | state
+    char *base = (char*) arena;
+    void *r = base, *Ap = base + vec_bytes, *state = base + 2 * vec_bytes;
+    char *pb[2] = {(char*) d->pbuf + HB_MAILBOX_BYTES, (char*) d->pbuf + HB_MAILBOX_BYTES + d->pbuf_ext_bytes};
+    peer_mailbox *mail = reinterpret_cast<peer_mailbox*>(d->pbuf);
+    cg_dhost *hstat = reinterpret_cast<cg_dhost*>(reinterpret_cast<char*>(ctx->hscalars) + 512);
+    void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 512;
+    hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
+    int grid = dgrid(ctx, n, DK_THREADS * 8);
+    if (grid < PK_MIN_GRID) grid = PK_MIN_GRID;
+    const bool fused = peer_env_fused_spmv() && hb_spmv_variant(A) == 3;
+    const peer_view *pv = d->pv_dev;
+
+    // p0 <- x0 (owned) + halo over NCCL; Ap = A x0; r = b - Ap; p0 = r; <r,r> all-reduced over NCCL (this also fences the
+    // previous solve's peer traffic from this one's); then the first halo push
+    void *p0 = pb[d->epoch & 1];
+    HB_CUDA(cudaMemcpyAsync(p0, x, es * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = hb_dist_halo_exchange(d, dtype, p0)) != HB_OK) return rc;
+    if ((rc = hb_spmv_internal(ctx, A, p0, Ap, nullptr)) != HB_OK) return rc;
+    HB_DISPATCH(dtype, {
+        cg_dstate<T> *st = (cg_dstate<T>*) state;
+        dcg_setup_kernel<T><<<dgrid(ctx, n, DK_THREADS * 4), DK_THREADS, 0, ctx->stream>>>(n, st, tol, max_iter, (const T*) b, (const T*) Ap, (T*) r, (T*) p0,
+                                                                                           ctx->partials, ctx->tickets + 6);
+        HB_LAUNCH_CHECK(ctx);
+        if ((rc = hb_dist_allreduce_sum(d, dtype, &st->rr, 1)) != HB_OK) return rc;
+        pcg_begin_kernel<T><<<HB_HALO_BLOCKS, DK_THREADS, 0, ctx->stream>>>(st, pv, d->epoch, d->send_idx, (const T*) p0);
+        HB_LAUNCH_CHECK(ctx);
+    });
+
+    cudaEvent_t ev[2];
+    HB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    const int batch = 8;
+    long long it = 0;
+    int status = HB_OK;
+    for (long long bidx = 0; status == HB_OK; bidx++){
+        for (int j = 0; j < batch && status == HB_OK; j++, it++){
+            const int parity = (int) (it & 1);
+            const unsigned long long g = d->epoch++;
+            void *p_old = pb[g & 1], *p_new = pb[(g + 1) & 1];
+            const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
+            HB_DISPATCH(dtype, {
+                cg_dstate<T> *st = (cg_dstate<T>*) state;
+                const bool vec = aligned16(x) && aligned16(r) && aligned16(Ap) && aligned16(p_old) && aligned16(p_new);
+                if (fused){
+                    ctx->peer_hook = pv; ctx->peer_epoch = g;
+                    status = hb_spmv_dot_internal(ctx, A, p_old, Ap, &st->pAp_local, &st->done[parity]);
+                    ctx->peer_hook = nullptr;
+                    if (status != HB_OK) break;
+                }else{
+                    peer_halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(pv, g, &st->done[parity]);
+                    ctx->launches++;
+                    if ((status = hb_spmv_dot_internal(ctx, A, p_old, Ap, &st->pAp_local, &st->done[parity])) != HB_OK) break;
+                    peer_publish_kernel<T><<<1, 32, 0, ctx->stream>>>(pv, HB_PEER_CH_PAP, g, &st->pAp_local, &st->done[parity]);
+                    ctx->launches++;
+                }
+                if (vec) pcg_update_kernel<T, true><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, (const T*) Ap, (T*) r, ctx->partials, ctx->tickets + 6, pv);
+                else     pcg_update_kernel<T, false><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, (const T*) Ap, (T*) r, ctx->partials, ctx->tickets + 6, pv);
+                ctx->launches++;
+                if (vec) pcg_direction_kernel<T, true><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
+                                                                                             pv, d->send_idx, (cg_dhost*) hstat_dev);
+                else     pcg_direction_kernel<T, false><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
+                                                                                              pv, d->send_idx, (cg_dhost*) hstat_dev);
+                ctx->launches++;
+            });
+        }
+        if (status != HB_OK) break;
+        if (cudaPeekAtLastError() != cudaSuccess){ status = hb_cuda_fail(cudaGetLastError(), "kernel launch"); break; }
+        if (cudaEventRecord(ev[bidx & 1], ctx->stream) != cudaSuccess){ status = hb_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
+        if (bidx > 0){
+            if (cudaEventSynchronize(ev[(bidx - 1) & 1]) != cudaSuccess){ status = hb_cuda_fail(cudaGetLastError(), "cudaEventSynchronize"); break; }
+            if (hstat->done) break;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (status != HB_OK) return status;
+    if (e != cudaSuccess) return hb_cuda_fail(e, "cudaStreamSynchronize");
+    int perr = 0;
+    HB_CUDA(cudaMemcpy(&perr, &mail->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr){
+        HB_CUDA(cudaMemset(&mail->error, 0, sizeof(int)));
+        hb_set_error("peer transport: a wait on a peer's flag timed out");
+        return HB_ERR_NCCL;
+    }
+    if (iters) *iters = hstat->iterations;
+    if (res) *res = hstat->rnorm;
+    return HB_OK;
+}
 }
 
 extern "C" {
@@ -193,9 +551,16 @@ int hb_dist_create(hb_ctx *ctx, int rank, int world, const void *id128, hb_dist 
 
 int hb_dist_destroy(hb_dist *d){
     if (!d) return HB_OK;
+    peer_release(d);
     if (d->sendbuf) cudaFree(d->sendbuf);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     delete d;
+    return HB_OK;
+}
+
+int hb_dist_transport(const hb_dist *d, int *transport){
+    HB_ARG(d && transport, "null");
+    *transport = (d->peer_state == 1) ? HB_TRANSPORT_PEER : HB_TRANSPORT_NCCL;
     return HB_OK;
 }
 
@@ -211,6 +576,14 @@ int hb_dist_set_plan(hb_dist *d, int n_owned, int n_ghost, int nneigh, const int
     HB_ARG(d, "dist is null");
     HB_ARG(n_owned >= 0 && n_ghost >= 0 && nneigh >= 0, "negative size");
     HB_ARG(nneigh == 0 || (neigh && send_count && recv_count), "null plan arrays");
+    if (d->peer_state == 1){                    // buffers were laid out for the previous plan; a new plan is set on all ranks together
+        HB_CUDA(cudaStreamSynchronize(d->ctx->stream));
+        int one = 1;
+        int rc = agree_min(d, &one);
+        if (rc != HB_OK) return rc;
+        peer_release(d);
+    }
+    d->peer_state = 0; d->plan_version++;
     d->n_owned = n_owned; d->n_ghost = n_ghost;
     d->neigh.assign(neigh, neigh + nneigh);
     d->send_count.assign(send_count, send_count + nneigh);
@@ -279,6 +652,13 @@ int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, 
     hb_ctx *ctx = d->ctx;
     const int n = d->n_owned, dtype = A->dtype;
     const size_t es = hb_dtype_size(dtype);
+    // transport: peer memory over NVLink when every rank can map every other one's exchange buffer (one NVLink domain),
+    // otherwise NCCL send/recv + all-reduce.  The choice is agreed by all ranks inside peer_setup.
+    if (d->world > 1 && d->world <= HB_MAX_PEERS && peer_env_enabled()){
+        int prc = peer_setup(d, es);
+        if (prc == HB_OK) return dist_cg_peer(d, A, b, x, tol, max_iter, iters, res);
+        if (prc != HB_ERR_UNSUPPORTED) return prc;
+    }
     const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256, ext_bytes = ((es * ((size_t) n + d->n_ghost) + 255) / 256) * 256;
     void *arena = nullptr;
     int rc;

@@ -8,29 +8,6 @@
 
 static constexpr int KR_THREADS = 256;
 
-// ------------------------------------------------------------------------------------------------ streaming loop
-// Grid-stride sweep over n elements: when VEC, 128-bit packets with U independent packets per array in flight per thread
-// (all loads of a batch are issued before the first dependent FMA), then the scalar tail; otherwise element by element.
-//   load(u, packet index) / finish(u, packet index) work on packet slot u;  scalar(element index) handles one element.
-template<typename T, bool VEC, int U, typename FL, typename FF, typename FS>
-__device__ __forceinline__ void stream_sweep(size_t n, FL load, FF finish, FS scalar){
-    const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    size_t done = 0;
-    if (VEC){
-        const size_t nvec = n / vec16<T>::N;
-        size_t i = gtid;
-        for (; i + (U - 1) * stride < nvec; i += U * stride){
-            #pragma unroll
-            for (int u = 0; u < U; u++) load(u, i + u * stride);
-            #pragma unroll
-            for (int u = 0; u < U; u++) finish(u, i + u * stride);
-        }
-        for (; i < nvec; i += stride){ load(0, i); finish(0, i); }
-        done = nvec * vec16<T>::N;
-    }
-    for (size_t j = done + gtid; j < n; j += stride) scalar(j);
-}
-
 // ------------------------------------------------------------------------------------------------ CG state (device)
 // zr[2] is double-buffered by iteration parity so that no kernel both reads and writes the same scalar.
 template<typename T> struct cg_state {

@@ -1,0 +1,151 @@
+// hb_peer.cuh — peer-memory transport of the row-partitioned solvers: every rank of one NVLink/NVSwitch domain maps the
+// others' exchange buffer (CUDA IPC) and the iteration kernels talk through it directly, so a CG iteration contains no
+// collective call at all:
+//   * halo:   the kernel that PRODUCES p stores the entries its neighbours need straight into their ghost slots
+//             (remote stores over NVLink, then one release flag per pushing block); the SpMV that consumes them waits on
+//             those flags in-kernel.
+//   * scalar sums (<p,Ap>, ||r||^2): the last block of the producing kernel stores this rank's partial into a slot of every
+//             peer's mailbox; every block of the consuming kernel waits for the W slots and adds them in rank order, so all
+//             ranks (and all blocks) get the same bits — the iteration stays in lock step without a host or NCCL round trip.
+// Slots and ghost buffers are double-buffered by the parity of a global iteration number g ("epoch"); a flag carries g + 1.
+// Why two buffers suffice: rank X can only write epoch g + 2 after it consumed a value of epoch g + 1 from every peer Y, and
+// Y published that value after the kernel in which it consumed epoch g (stream order).  The first exchanges of a solve go
+// through NCCL (halo of x0, all-reduce of <r,r>), which also fences one solve from the next.
+#pragma once
+#include "hb_common.cuh"
+
+static constexpr int HB_MAX_PEERS   = 16;      // ranks of one NVLink domain (8 on an HGX B200 board)
+static constexpr int HB_MAX_NEIGH   = 8;       // halo neighbours per rank on this path (1-D row blocks of a stencil: 2)
+static constexpr int HB_HALO_BLOCKS = 32;      // blocks that push the halo, each signalling its own flag
+static constexpr int HB_PEER_CH_PAP = 0, HB_PEER_CH_RR = 1;
+
+struct peer_slot { double v[2]; unsigned long long seq; unsigned long long pad; };              // 32 B
+// mailbox at the start of every rank's exchange buffer
+struct peer_mailbox {
+    peer_slot slot[2][2][HB_MAX_PEERS];                             // [channel][epoch parity][source rank]
+    unsigned long long halo_seq[HB_MAX_PEERS][HB_HALO_BLOCKS];      // [source rank][pushing block] = epoch + 1 of the last push
+    int error;                                                      // set when a wait timed out (peer died / mis-sequenced)
+    int pad[15];
+};
+static constexpr size_t HB_MAILBOX_BYTES = 8192;
+static_assert(sizeof(peer_mailbox) <= HB_MAILBOX_BYTES, "mailbox layout");
+
+// what a kernel needs to reach its peers (lives in device memory, built by peer_setup)
+struct peer_view {
+    int rank, world, nneigh, pad;
+    peer_mailbox *mail[HB_MAX_PEERS];           // mailbox of rank q as mapped here (q == rank: the local one)
+    int neigh[HB_MAX_NEIGH];                    // rank of halo neighbour k
+    int recv_from[HB_MAX_NEIGH];                // 1 when neighbour k sends us ghost entries
+    int send_off[HB_MAX_NEIGH + 1];             // neighbour k receives send_idx[send_off[k] .. send_off[k+1])
+    char *ghost_dst[HB_MAX_NEIGH][2];           // where OUR entries land in neighbour k's p buffer of parity 0/1 (mapped here)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v){
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p){
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p){
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= target; gives up after ~4 s of GPU clock (a peer that died must not hang this GPU): returns false
+__device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long target){
+    if (ld_acquire_sys(flag) >= target) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < target){
+        __nanosleep(40);
+        if (clock64() - t0 > 8000000000LL) return false;
+    }
+    return true;
+}
+
+template<typename T> __device__ __forceinline__ void slot_pack(T v, double &a, double &b);
+template<> __device__ __forceinline__ void slot_pack<float>(float v, double &a, double &b){ a = (double) v; b = 0.0; }
+template<> __device__ __forceinline__ void slot_pack<double>(double v, double &a, double &b){ a = v; b = 0.0; }
+template<> __device__ __forceinline__ void slot_pack<cplx<float>>(cplx<float> v, double &a, double &b){ a = (double) v.re; b = (double) v.im; }
+template<> __device__ __forceinline__ void slot_pack<cplx<double>>(cplx<double> v, double &a, double &b){ a = v.re; b = v.im; }
+template<typename T> __device__ __forceinline__ T slot_unpack(double a, double b);
+template<> __device__ __forceinline__ float  slot_unpack<float>(double a, double){ return (float) a; }
+template<> __device__ __forceinline__ double slot_unpack<double>(double a, double){ return a; }
+template<> __device__ __forceinline__ cplx<float>  slot_unpack<cplx<float>>(double a, double b){ return {(float) a, (float) b}; }
+template<> __device__ __forceinline__ cplx<double> slot_unpack<cplx<double>>(double a, double b){ return {a, b}; }
+
+// Called by (at least) the first warp of ONE block, all 32 lanes converged: lane q < world stores `value` into rank q's mailbox
+// slot [channel][g & 1][our rank] and releases it with seq = g + 1.  `value` must be the same in every calling lane.
+template<typename T> __device__ __forceinline__ void peer_publish(const peer_view *pv, int channel, unsigned long long g, T value){
+    const int q = threadIdx.x;
+    if (q < pv->world){
+        peer_slot *s = &pv->mail[q]->slot[channel][g & 1][pv->rank];
+        double a, b;
+        slot_pack<T>(value, a, b);
+        volatile double *sv = s->v;
+        sv[0] = a; sv[1] = b;
+        __threadfence_system();
+        st_release_sys(&s->seq, g + 1);
+    }
+}
+// Called by the first warp of a block (threadIdx.x < 32, converged): waits for the W partials of (channel, g) in the LOCAL
+// mailbox and returns their sum in rank order (bit-identical on every rank and block) in all 32 lanes.  A timed-out wait marks
+// the mailbox and yields NaN, which the solvers' stop test turns into an orderly stop on every rank.
+template<typename T> __device__ __forceinline__ T peer_wait_sum(const peer_view *pv, int channel, unsigned long long g){
+    const int q = threadIdx.x & 31, W = pv->world;
+    peer_mailbox *mine = pv->mail[pv->rank];
+    double a = 0.0, b = 0.0;
+    bool ok = true;
+    for (int s0 = q; s0 < W; s0 += 32){         // W <= 16: one trip
+        const peer_slot *s = &mine->slot[channel][g & 1][s0];
+        ok = peer_spin(&s->seq, g + 1);
+        a = ld_volatile_f64(&s->v[0]); b = ld_volatile_f64(&s->v[1]);
+    }
+    if (!__all_sync(0xffffffffu, ok)){
+        if (q == 0) mine->error = 1;
+        a = b = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    double sa = 0.0, sb = 0.0;
+    for (int s0 = 0; s0 < W; s0++){             // rank order, sequential: deterministic
+        sa += __shfl_sync(0xffffffffu, a, s0);
+        sb += __shfl_sync(0xffffffffu, b, s0);
+    }
+    return slot_unpack<T>(sa, sb);
+}
+// Called by the first warp of a block (converged): waits until every neighbour that sends us ghosts has released all of its
+// HB_HALO_BLOCKS flags for epoch g.  Returns false on time-out (mailbox marked).
+__device__ __forceinline__ bool peer_halo_wait(const peer_view *pv, unsigned long long g){
+    const int lane = threadIdx.x & 31;
+    peer_mailbox *mine = pv->mail[pv->rank];
+    bool ok = true;
+    for (int k = 0; k < pv->nneigh; k++){
+        if (!pv->recv_from[k]) continue;
+        for (int b = lane; b < HB_HALO_BLOCKS; b += 32)
+            ok = peer_spin(&mine->halo_seq[pv->neigh[k]][b], g + 1) && ok;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok && lane == 0) mine->error = 1;
+    return ok;
+}
+// Halo push by blocks 0 .. HB_HALO_BLOCKS-1 of a grid (every thread of those blocks calls it, converged per block).
+// value(j) = the new p entry at local index send_idx[j]; entry j of the concatenated send list goes to neighbour k with
+// send_off[k] <= j < send_off[k+1], into its ghost slot of buffer parity (g & 1).  Each block then releases its flag g + 1 in
+// every neighbour's mailbox (blocks with an empty chunk as well: the receiver counts flags, not data).
+template<typename T, typename F>
+__device__ __forceinline__ void peer_halo_push(const peer_view *pv, unsigned long long g, F value){
+    if (blockIdx.x >= HB_HALO_BLOCKS) return;
+    const int total = pv->send_off[pv->nneigh];
+    const int chunk = (total + HB_HALO_BLOCKS - 1) / HB_HALO_BLOCKS;
+    const int j0 = blockIdx.x * chunk, j1 = min(j0 + chunk, total);
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x){
+        int k = 0;
+        while (j >= pv->send_off[k + 1]) k++;
+        T *dst = reinterpret_cast<T*>(pv->ghost_dst[k][g & 1]) + (j - pv->send_off[k]);
+        *dst = value(j);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pv->nneigh && pv->send_off[threadIdx.x + 1] > pv->send_off[threadIdx.x])
+        st_release_sys(&pv->mail[pv->neigh[threadIdx.x]]->halo_seq[pv->rank][blockIdx.x], g + 1);
+}

@@ -317,7 +317,8 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                                             A->pipe_contiguous ? A->cta_rows[CFG] : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip,
-                                                            (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols);
+                                                            (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols,
+                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -363,13 +364,17 @@ static int pipe_occupancy_any(int cfg, int tpr, int dtype){
 }
 
 // variant: 0 auto, 1 row-vector, 2 staged tiles, 3 streaming pipeline (bulk-async ring)
+int hb_spmv_variant(const hb_csr *A){
+    int variant = A->variant;
+    const bool pipe_ok = A->vec_aligned && A->cta_rows[A->pipe_cfg] != nullptr && A->nnz > 0;
+    if (variant == 0) variant = (A->mean_row_nnz > 112.0) ? 1 : (pipe_ok ? 3 : 2);
+    if (variant == 3 && !pipe_ok) variant = 2;
+    return variant;
+}
 template<typename T, bool DOT>
 int hb_spmv_n_typed(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
-    int variant = A->variant;
+    const int variant = hb_spmv_variant(A);
     const double mean = A->mean_row_nnz;
-    const bool pipe_ok = A->vec_aligned && A->cta_rows[A->pipe_cfg] != nullptr && A->nnz > 0;
-    if (variant == 0) variant = (mean > 112.0) ? 1 : (pipe_ok ? 3 : 2);
-    if (variant == 3 && !pipe_ok) variant = 2;
     if (variant == 3){
         if (A->pipe_cfg == 0) return launch_pipe<T, 0, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         return launch_pipe<T, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);

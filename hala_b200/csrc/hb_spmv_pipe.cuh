@@ -18,6 +18,7 @@
 // memory, long rows by the whole CTA.
 #pragma once
 #include "hb_common.cuh"
+#include "hb_peer.cuh"
 
 // ring capacity per stage = THREADS * pipe_slots<T>() non-zeros; entries per lane per batch = the same number
 template<typename T> __host__ __device__ constexpr int pipe_slots(){ return sizeof(T) == 16 ? 4 : 8; }
@@ -74,7 +75,8 @@ template<typename T, int THREADS, int TPR, int STAGES, bool DOT>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
-                                                            void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols){
+                                                            void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
+                                                            const peer_view *pv, unsigned long long epoch){
     constexpr int ROWS = THREADS / TPR;
     constexpr int CAP  = THREADS * pipe_slots<T>();
     constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
@@ -89,6 +91,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     __shared__ T        red[32];
 
     if (skip_flag && *skip_flag) return;
+    // row-partitioned run over peer memory: the ghost entries of x are being stored by the neighbours' direction kernels;
+    // wait for their flags before the first gather (the matrix stream itself does not depend on them)
+    if (pv){
+        if (threadIdx.x < 32) peer_halo_wait(pv, epoch);
+        __syncthreads();
+    }
 
     const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
     const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
@@ -285,7 +293,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
         if (tid == 0) partials[blockIdx.x] = b;
         if (last_block_arrives(ticket)){
             T total = sum_partials<T>(partials, gridDim.x, 1, red);
-            if (tid == 0) *dot_out = total;
+            if (tid == 0){ *dot_out = total; red[0] = total; }
+            if (pv){                                            // hand this rank's partial to every peer (hb_peer.cuh)
+                __syncthreads();
+                if (tid < 32) peer_publish<T>(pv, HB_PEER_CH_PAP, epoch, red[0]);
+            }
         }
     }
 }

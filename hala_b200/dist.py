@@ -16,6 +16,7 @@ DIST_SIGNATURES = {
     "hb_dist_create": (_i, [_vp, _i, _i, _vp, _pvp]),
     "hb_dist_destroy": (_i, [_vp]),
     "hb_dist_info": (_i, [_vp, _pi, _pi]),
+    "hb_dist_transport": (_i, [_vp, _pi]),
     "hb_dist_set_plan": (_i, [_vp, _i, _i, _i, _pi, _pi, _pi, _vp]),
     "hb_dist_halo_exchange": (_i, [_vp, _i, _vp]),
     "hb_dist_allreduce_sum": (_i, [_vp, _i, _vp, _i]),
@@ -60,6 +61,12 @@ class Communicator:
         it, res = C.c_int(0), C.c_double(0)
         check(lib.hb_dist_cg(self.h, csr.h, b_ptr, x_ptr, float(tol), int(max_iter), C.byref(it), C.byref(res)), "hb_dist_cg")
         return it.value, res.value
+
+    def transport(self):
+        """'peer' (NVLink peer memory, no collective call per iteration) or 'nccl' — what the last cg() on this plan used"""
+        t = C.c_int(0)
+        check(lib.hb_dist_transport(self.h, C.byref(t)), "hb_dist_transport")
+        return "peer" if t.value == 1 else "nccl"
 
     def gmres(self, csr, b_ptr, x_ptr, tol, max_outer, restart, cproj=0):
         it, res = C.c_int(0), C.c_double(0)
@@ -164,7 +171,9 @@ def run_bench(args, slab, ClockSampler, measured_peak):
         line = {"metric": "cg_iters_per_s", "value": its, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"lap3d7-{n} fp64 unpreconditioned CG, b=1/sqrt(N), x0=0 (BASELINE configs[2])", "rows": N, "nnz": nnz,
-                           "parallelism": f"{world} ranks, 1-D row blocks, ghost halo (ncclSend/Recv) + 2 scalar all-reduces per iteration",
+                           "parallelism": (f"{world} ranks, 1-D row blocks; transport=peer: halo entries and the 2 scalar partials per iteration are stored into the "
+                                           "peers' memory over NVLink by the iteration kernels (no collective call)" if comm.transport() == "peer" else
+                                           f"{world} ranks, 1-D row blocks; transport=nccl: ghost halo (ncclSend/Recv) + 2 scalar all-reduces per iteration"),
                            "l2": "inputs larger than L2; no flush", "step": "one CG iteration", "max_ghosts_per_rank": int(halo.item())},
                 "gbs": Bcg * its / 1e9, "frac_of_measured_peak": Bcg * its / 1e9 / (peak * world), "algorithmic_bytes_per_step": Bcg, "final_residual": res,
                 "roofline": {"bound": "hbm", "kernel": "spmv_pipe_kernel<double,...,DOT> on one rank's slab", "achieved": Bk / kms / 1e6, "peak": peak,

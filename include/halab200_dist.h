@@ -21,6 +21,12 @@ int hb_dist_unique_id(void *id128);
 int hb_dist_create(hb_ctx *ctx, int rank, int world, const void *id128, hb_dist **dist);
 int hb_dist_destroy(hb_dist *dist);
 int hb_dist_info(const hb_dist *dist, int *rank, int *world);
+/* which transport the last hb_dist_cg on the current plan used: peer memory (every rank maps every other rank's exchange
+ * buffer through CUDA IPC; halo entries and scalar partials are stored straight into the peers' memory over NVLink by the
+ * iteration kernels, no collective call per iteration) or NCCL (send/recv + all-reduce).  Peer is chosen when all ranks can
+ * map each other (one NVLink domain, <= 16 ranks, <= 8 halo neighbours); HB_DIST_PEER=0 in the environment forces NCCL. */
+enum { HB_TRANSPORT_NCCL = 0, HB_TRANSPORT_PEER = 1 };
+int hb_dist_transport(const hb_dist *dist, int *transport);
 
 /* Exchange plan of this rank.  n_owned rows/columns are owned; ghost columns are numbered n_owned .. n_owned + n_ghost - 1
  * in the order they are received: neighbour 0's block first, then neighbour 1's, ...
@@ -37,8 +43,8 @@ int hb_dist_allreduce_sum(hb_dist *dist, int dtype, void *dev_scalars, int count
 
 /* Row-partitioned CG.  csr = local rows with columns renumbered to [owned | ghosts] (cols == n_owned + n_ghost);
  * b, x = owned parts.  Same recurrence, counter and stop test as hb_cg; per iteration: halo exchange of p, SpMV fused with
- * the local <p,Ap>, all-reduce, fused update + local ||r||^2, all-reduce, direction update.  All ranks return the same
- * iteration count and residual.                                                                                            */
+ * the local <p,Ap>, sum over ranks, fused update + local ||r||^2, sum over ranks, x and direction update.  All ranks
+ * return the same iteration count and residual (the sums are formed in rank order on every rank).                                                                                          */
 int hb_dist_cg(hb_dist *dist, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, int *iters, double *res);
 /* Row-partitioned GMRES(m): hb_gmres with the halo of each basis vector exchanged in place before its SpMV, the k Gram-Schmidt
  * coefficients and the norm all-reduced (k + 1 scalars per inner iteration), Givens/Hessenberg replicated on every host. */

@@ -52,8 +52,16 @@ def main():
         x.zero_()
         it2, _ = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), 0.0, 11)
         assert it2 == 11, it2
+        want = os.environ.get("HB_EXPECT_TRANSPORT")
+        if want:
+            assert comm.transport() == want, (comm.transport(), want)
+        # --- a second solve from a non-zero initial guess (x0 halo over NCCL, epochs continue): converges in <= the first count
+        x.copy_(torch.from_numpy(xo[lo:hi]).to(dev) * 0.5)
+        it3, res3 = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tol, 10 ** 6)
+        assert res3 < tol and it3 <= it + 2, (it3, it, res3)
+        assert np.max(np.abs(x.cpu().numpy() - xo[lo:hi])) < 1e-6, name
         if rank == 0:
-            print(f"dist ok: {name}:{n} world={world} cg {it} its (oracle {ito}), ghosts {n_ghost}", flush=True)
+            print(f"dist ok: {name}:{n} world={world} transport={comm.transport()} cg {it} its (oracle {ito}), ghosts {n_ghost}", flush=True)
         del prob
     # --- row-partitioned GMRES(20) on the nonsymmetric convection-diffusion matrix against the oracle
     name, n, tol = "convdiff7", 20, 1e-8
