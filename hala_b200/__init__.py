@@ -7,4 +7,5 @@ tests and bench.py. Importing it without the built library fails loudly: there i
 from . import matgen  # noqa: F401  (numpy only)
 from .capi import HalaB200Error, LIB_PATH  # noqa: F401
 from .engine import (gpu_device_count, gpu_engine, gpu_vector, gpu_sparse_matrix, make_sparse_matrix,  # noqa: F401
-                     vcopy, axpy, scal, dot, dotu, norm2, gemv, sparse_gemv, solve_cg, solve_gmres)
+                     vcopy, axpy, scal, dot, dotu, norm2, asum, vswap, iamax, rot, rotg, rotm, rotmg, gemv, sparse_gemv,
+                     solve_cg, solve_gmres)

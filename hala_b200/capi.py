@@ -62,6 +62,12 @@ SIGNATURES = {
     "hb_dot": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "hb_nrm2": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hb_asum": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "hb_swap": (_i, [_vp, _i, _i, _vp, _i, _vp, _i]),
+    "hb_iamax": (_i, [_vp, _i, _i, _vp, _i, _pi]),
+    "hb_rot": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i]),
+    "hb_rotm": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "hb_rotg": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "hb_rotmg": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hb_gemv": (_i, [_vp, _i, C.c_char, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]),
     "hb_multi_dot": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "hb_multi_axpy_nrm2": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _vp]),

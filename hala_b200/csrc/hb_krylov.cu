@@ -176,48 +176,62 @@ __global__ void __launch_bounds__(KR_THREADS) xpby_kernel(int n, const T * __res
 }
 
 // ------------------------------------------------------------------------------------------------ GMRES: multi-dot
-// h[c] = sum_i op(W[i,c]) r[i] for c < k in ONE pass: each thread keeps RPT rows of r in registers and walks the k
-// columns; per column a warp-shuffle reduction feeds a per-warp shared accumulator, so r is read once and every column
-// of W once.  Block partials -> last block sums them in fixed order.
-static constexpr int MD_RPT  = 4;          // rows per thread per sweep
+// h[c] = sum_i op(W[i,c]) r[i] for c < k.  Columns are taken MD_KC at a time: each thread keeps MD_KC running sums in
+// registers while it sweeps its rows (128-bit packets of r and of the MD_KC columns, all loads of a step issued before the
+// first FMA), so a column costs one load and one FMA per element and the reductions happen once per chunk, not once per
+// row block.  W is read exactly once; r once per chunk of columns ((k + ceil(k/KC)) N s bytes in all; r mostly from L2).
+// Block partials -> the last block sums them in fixed order (bit-reproducible).
 static constexpr int MD_KMAX = 64;         // columns handled per launch (restart <= 64 in one launch; more -> several launches)
+template<typename T> __host__ __device__ constexpr int md_kc(){ return sizeof(T) == 16 ? 8 : 16; }
 
-template<typename T, bool CONJ>
-__global__ void __launch_bounds__(KR_THREADS) multi_dot_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T * __restrict__ r,
-                                                               void *partials_v, unsigned int *ticket, T *h_out, const int *skip_flag){
-    __shared__ T acc[MD_KMAX][KR_THREADS / 32];
+template<typename T, bool CONJ, bool VEC>
+__global__ void __launch_bounds__(KR_THREADS, 2) multi_dot_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T * __restrict__ r,
+                                                                  void *partials_v, unsigned int *ticket, T *h_out, const int *skip_flag){
+    constexpr int KC = md_kc<T>();
+    constexpr int NP = VEC ? vec16<T>::N : 1;                  // elements per packet
     __shared__ T red[32];
     if (skip_flag && *skip_flag) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = threadIdx.x; c < MD_KMAX * (KR_THREADS / 32); c += blockDim.x) (&acc[0][0])[c] = zero_of<T>();
-    __syncthreads();
-    const long long sweep = (long long) gridDim.x * KR_THREADS * MD_RPT;
-    for (long long base = (long long) blockIdx.x * KR_THREADS * MD_RPT; base < rows; base += sweep){
-        T rv[MD_RPT]; long long idx[MD_RPT];
+    T *partials = reinterpret_cast<T*>(partials_v);             // layout [block][k]
+    const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    const size_t npk = (size_t) rows / NP;
+    for (int c0 = 0; c0 < k; c0 += KC){
+        const int kc = min(KC, k - c0);
+        T acc[KC];
         #pragma unroll
-        for (int u = 0; u < MD_RPT; u++){
-            idx[u] = base + (long long) u * KR_THREADS + threadIdx.x;
-            rv[u] = (idx[u] < rows) ? r[idx[u]] : zero_of<T>();
-        }
-        for (int c = 0; c < k; c++){
-            const T *col = W + (size_t) c * ldw;
-            T w[MD_RPT];
+        for (int j = 0; j < KC; j++) acc[j] = zero_of<T>();
+        const T *Wc = W + (size_t) c0 * ldw;
+        for (size_t i = gtid; i < npk; i += stride){
+            T rv[NP], wv[KC][NP];
+            if (VEC){
+                *reinterpret_cast<vec16<T>*>(rv) = reinterpret_cast<const vec16<T>*>(r)[i];
+                #pragma unroll
+                for (int j = 0; j < KC; j++)
+                    if (j < kc) *reinterpret_cast<int4*>(wv[j]) = __ldcs(reinterpret_cast<const int4*>(Wc + (size_t) j * ldw) + i);
+            }else{
+                rv[0] = r[i];
+                #pragma unroll
+                for (int j = 0; j < KC; j++) if (j < kc) wv[j][0] = ld_stream(Wc + (size_t) j * ldw + i);
+            }
             #pragma unroll
-            for (int u = 0; u < MD_RPT; u++) w[u] = (idx[u] < rows) ? ld_stream(col + idx[u]) : zero_of<T>();
-            T part = zero_of<T>();
-            #pragma unroll
-            for (int u = 0; u < MD_RPT; u++) part = hfma(CONJ ? hconj(w[u]) : w[u], rv[u], part);
-            part = warp_sum(part);
-            if (lane == 0) acc[c][warp] = hadd(acc[c][warp], part);
+            for (int j = 0; j < KC; j++) if (j < kc){
+                #pragma unroll
+                for (int e = 0; e < NP; e++) acc[j] = hfma(CONJ ? hconj(wv[j][e]) : wv[j][e], rv[e], acc[j]);
+            }
         }
-    }
-    __syncthreads();
-    T *partials = reinterpret_cast<T*>(partials_v);     // layout [block][k]
-    for (int c = threadIdx.x; c < k; c += blockDim.x){
-        T s = zero_of<T>();
+        if (VEC){                                               // scalar tail behind the last whole packet
+            for (size_t i = npk * NP + gtid; i < (size_t) rows; i += stride){
+                const T ri = r[i];
+                #pragma unroll
+                for (int j = 0; j < KC; j++) if (j < kc){ const T w = Wc[(size_t) j * ldw + i]; acc[j] = hfma(CONJ ? hconj(w) : w, ri, acc[j]); }
+            }
+        }
         #pragma unroll
-        for (int w = 0; w < KR_THREADS / 32; w++) s = hadd(s, acc[c][w]);
-        partials[(size_t) blockIdx.x * k + c] = s;
+        for (int j = 0; j < KC; j++){
+            if (j < kc){                                        // block-uniform
+                T s = block_sum(acc[j], red);
+                if (threadIdx.x == 0) partials[(size_t) blockIdx.x * k + c0 + j] = s;
+            }
+        }
     }
     if (last_block_arrives(ticket)){
         for (int c = 0; c < k; c++){
@@ -227,30 +241,71 @@ __global__ void __launch_bounds__(KR_THREADS) multi_dot_kernel(long long rows, i
     }
 }
 
-// r -= W h ; nrm2sq = sum |r_i|^2 of the updated r (same pass). h (k scalars) is read from device memory into shared.
-template<typename T>
-__global__ void __launch_bounds__(KR_THREADS) multi_axpy_nrm2_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T *h_dev,
-                                                                     T *r, void *partials_v, unsigned int *ticket, T *nrm2sq_out, const int *skip_flag,
-                                                                     T scale_h){
+// r += scale * W h ; nrm2sq = sum |r_i|^2 of the updated r (same pass). h (k scalars) is read from device memory into shared.
+// Two 128-bit packets of r per thread; the columns are taken eight at a time with all sixteen loads issued before the FMAs.
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(KR_THREADS, 2) multi_axpy_nrm2_kernel(long long rows, int k, const T * __restrict__ W, size_t ldw, const T *h_dev,
+                                                                        T *r, void *partials_v, unsigned int *ticket, T *nrm2sq_out, const int *skip_flag,
+                                                                        T scale_h){
+    constexpr int NP = VEC ? vec16<T>::N : 1, U = 2, CG = 8;
     __shared__ T h[MD_KMAX];
     __shared__ double red[32];
     if (skip_flag && *skip_flag) return;
     for (int c = threadIdx.x; c < k; c += blockDim.x) h[c] = hmul(scale_h, h_dev[c]);
     __syncthreads();
     double acc = 0.0;
-    const long long sweep = (long long) gridDim.x * KR_THREADS * 2;
-    for (long long base = (long long) blockIdx.x * KR_THREADS * 2; base < rows; base += sweep){
-        const long long i0 = base + threadIdx.x, i1 = i0 + KR_THREADS;
-        T t0 = (i0 < rows) ? r[i0] : zero_of<T>(), t1 = (i1 < rows) ? r[i1] : zero_of<T>();
-        #pragma unroll 4
-        for (int c = 0; c < k; c++){
-            const T *col = W + (size_t) c * ldw;
-            T w0 = (i0 < rows) ? ld_stream(col + i0) : zero_of<T>();
-            T w1 = (i1 < rows) ? ld_stream(col + i1) : zero_of<T>();
-            t0 = hfma(w0, h[c], t0); t1 = hfma(w1, h[c], t1);
+    const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    const size_t npk = (size_t) rows / NP;
+    for (size_t i0 = gtid; i0 < npk; i0 += U * stride){
+        const size_t i1 = i0 + stride;
+        const bool two = i1 < npk;
+        T t[U][NP];
+        if (VEC){
+            *reinterpret_cast<vec16<T>*>(t[0]) = reinterpret_cast<const vec16<T>*>(r)[i0];
+            if (two) *reinterpret_cast<vec16<T>*>(t[1]) = reinterpret_cast<const vec16<T>*>(r)[i1];
+        }else{
+            t[0][0] = r[i0];
+            if (two) t[1][0] = r[i1];
         }
-        if (i0 < rows){ r[i0] = t0; acc += (double) habs2(t0); }
-        if (i1 < rows){ r[i1] = t1; acc += (double) habs2(t1); }
+        for (int c0 = 0; c0 < k; c0 += CG){
+            T w[CG][U][NP];
+            #pragma unroll
+            for (int j = 0; j < CG; j++) if (c0 + j < k){
+                const T *col = W + (size_t) (c0 + j) * ldw;
+                if (VEC){
+                    *reinterpret_cast<int4*>(w[j][0]) = __ldcs(reinterpret_cast<const int4*>(col) + i0);
+                    if (two) *reinterpret_cast<int4*>(w[j][1]) = __ldcs(reinterpret_cast<const int4*>(col) + i1);
+                }else{
+                    w[j][0][0] = ld_stream(col + i0);
+                    if (two) w[j][1][0] = ld_stream(col + i1);
+                }
+            }
+            #pragma unroll
+            for (int j = 0; j < CG; j++) if (c0 + j < k){
+                const T hc = h[c0 + j];
+                #pragma unroll
+                for (int e = 0; e < NP; e++){
+                    t[0][e] = hfma(w[j][0][e], hc, t[0][e]);
+                    if (two) t[1][e] = hfma(w[j][1][e], hc, t[1][e]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int e = 0; e < NP; e++){ acc += (double) habs2(t[0][e]); if (two) acc += (double) habs2(t[1][e]); }
+        if (VEC){
+            reinterpret_cast<vec16<T>*>(r)[i0] = *reinterpret_cast<vec16<T>*>(t[0]);
+            if (two) reinterpret_cast<vec16<T>*>(r)[i1] = *reinterpret_cast<vec16<T>*>(t[1]);
+        }else{
+            r[i0] = t[0][0];
+            if (two) r[i1] = t[1][0];
+        }
+    }
+    if (VEC){
+        for (size_t i = npk * NP + gtid; i < (size_t) rows; i += stride){
+            T ti = r[i];
+            for (int c = 0; c < k; c++) ti = hfma(W[(size_t) c * ldw + i], h[c], ti);
+            r[i] = ti; acc += (double) habs2(ti);
+        }
     }
     if (nrm2sq_out){
         double *partials = reinterpret_cast<double*>(partials_v);
@@ -333,17 +388,19 @@ static inline int kr_grid(const hb_ctx *ctx, long long n, int per_block){
     return (int) (need < cap ? need : cap);
 }
 
+#define HB_MD_LAUNCH(CJ, VC) multi_dot_kernel<T, CJ, VC><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip)
 int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int k, const void *W, size_t ldw, const void *r, void *h_dev, const int *skip){
     for (int c0 = 0; c0 < k; c0 += MD_KMAX){
         const int kk = (k - c0 < MD_KMAX) ? (k - c0) : MD_KMAX;
-        int grid = kr_grid(ctx, rows, KR_THREADS * MD_RPT);
         HB_DISPATCH(dtype, {
             const T *Wc = (const T*) W + (size_t) c0 * ldw;
             T *hc = (T*) h_dev + c0;
-            if (conj && is_cplx<T>::value)
-                multi_dot_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip);
-            else
-                multi_dot_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip);
+            const bool vec = aligned16(Wc) && aligned16(r) && (ldw * sizeof(T)) % 16 == 0;
+            // one wave of 2 CTAs per SM; a packet per thread per step
+            int grid = hb_grid_for(ctx, (size_t) (rows > 0 ? rows : 1), KR_THREADS * (vec ? vec16<T>::N : 1), 2);
+            const bool cj = conj && is_cplx<T>::value;
+            if (cj){ if (vec) HB_MD_LAUNCH(true, true); else HB_MD_LAUNCH(true, false); }
+            else   { if (vec) HB_MD_LAUNCH(false, true); else HB_MD_LAUNCH(false, false); }
         });
         HB_LAUNCH_CHECK(ctx);
     }
@@ -356,10 +413,14 @@ int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const 
     for (int c0 = 0; c0 < k || c0 == 0; c0 += MD_KMAX){     // k == 0 still launches once: it delivers the norm
         const int kk = (k - c0 < MD_KMAX) ? (k - c0) : MD_KMAX;
         const bool last = (c0 + kk >= k);
-        int grid = kr_grid(ctx, rows, KR_THREADS * 2);
         HB_DISPATCH(dtype, {
-            multi_axpy_nrm2_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, (const T*) W + (size_t) c0 * ldw, ldw, (const T*) h_dev + c0,
-                (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));
+            const T *Wc = (const T*) W + (size_t) c0 * ldw;
+            const bool vec = aligned16(r) && (kk == 0 || (aligned16(Wc) && (ldw * sizeof(T)) % 16 == 0));
+            int grid = hb_grid_for(ctx, (size_t) (rows > 0 ? rows : 1), KR_THREADS * 2 * (vec ? vec16<T>::N : 1), 2);
+            if (vec) multi_axpy_nrm2_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) h_dev + c0,
+                        (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));
+            else     multi_axpy_nrm2_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) h_dev + c0,
+                        (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));
         });
         HB_LAUNCH_CHECK(ctx);
     }

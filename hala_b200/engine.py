@@ -202,6 +202,57 @@ def norm2(engine, x, incx=1, N=-1):
     return res[0]
 
 
+def asum(engine, x, incx=1, N=-1):
+    n = _default_n(x, incx, N)
+    res = np.zeros(1, dtype=_REAL[x.dtype])
+    check(lib.hb_asum(engine.ctx, _CODE[x.dtype], n, x.ptr, incx, _host_ptr(res)), "hb_asum")
+    return res[0]
+
+
+def vswap(engine, x, y, incx=1, incy=1, N=-1):
+    n = _default_n(x, incx, N)
+    check(lib.hb_swap(engine.ctx, _CODE[x.dtype], n, x.ptr, incx, y.ptr, incy), "hb_swap")
+
+
+def iamax(engine, x, incx=1, N=-1):
+    """0-based index of the first entry with the largest |re| + |im| (reference returns cublas' 1-based result minus one)"""
+    n = _default_n(x, incx, N)
+    res = C.c_int(0)
+    check(lib.hb_iamax(engine.ctx, _CODE[x.dtype], n, x.ptr, incx, C.byref(res)), "hb_iamax")
+    return res.value - 1
+
+
+def rotg(engine, a, b, dtype=np.float64):
+    """Givens rotation of (a, b): returns (r, z, c, s) with netlib semantics"""
+    dt = np.dtype(dtype)
+    va, vb, vs = _sc(a, dt), _sc(b, dt), np.zeros(1, dtype=dt)
+    vc = np.zeros(1, dtype=_REAL[dt])
+    check(lib.hb_rotg(engine.ctx, _CODE[dt], _host_ptr(va), _host_ptr(vb), _host_ptr(vc), _host_ptr(vs)), "hb_rotg")
+    return va[0], vb[0], vc[0], vs[0]
+
+
+def rot(engine, x, y, c, s, incx=1, incy=1, N=-1):
+    n = _default_n(x, incx, N)
+    real_s = np.iscomplexobj(np.zeros(1, x.dtype)) and not np.iscomplexobj(s)
+    vc = _sc(c, _REAL[x.dtype])
+    vs = _sc(s, _REAL[x.dtype] if real_s else x.dtype)
+    check(lib.hb_rot(engine.ctx, _CODE[x.dtype], n, x.ptr, incx, y.ptr, incy, _host_ptr(vc), _host_ptr(vs), 1 if real_s else 0), "hb_rot")
+
+
+def rotmg(engine, d1, d2, x1, y1, param, dtype=np.float64):
+    """modified Givens setup; param: numpy array of 5 (updated in place); returns (d1, d2, x1)"""
+    dt = np.dtype(dtype)
+    v = [_sc(t, dt) for t in (d1, d2, x1, y1)]
+    check(lib.hb_rotmg(engine.ctx, _CODE[dt], _host_ptr(v[0]), _host_ptr(v[1]), _host_ptr(v[2]), _host_ptr(v[3]), _host_ptr(param)), "hb_rotmg")
+    return v[0][0], v[1][0], v[2][0]
+
+
+def rotm(engine, x, y, param, incx=1, incy=1, N=-1):
+    n = _default_n(x, incx, N)
+    prm = np.ascontiguousarray(param, dtype=x.dtype)
+    check(lib.hb_rotm(engine.ctx, _CODE[x.dtype], n, x.ptr, incx, y.ptr, incy, _host_ptr(prm)), "hb_rotm")
+
+
 def gemv(engine, trans, M, N, alpha, A, x, beta, y, lda=-1, incx=1, incy=1):
     lda = M if lda < 0 else lda
     dt = A.dtype

@@ -71,6 +71,21 @@ inline void dgmm(gpu_engine const &engine, char side, int M, int N, VectorLikeA 
                  VectorLikeB const &x, VectorLikeC &&C, int lda = -1, int incx = 1, int ldc = -1){
     dgmm(engine, side, M, N, A, lda, x, incx, C, ldc);
 }
+template<class VectorLikeX, class VectorLikeY>
+inline void vswap(gpu_engine const &engine, VectorLikeX &&x, VectorLikeY &&y, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    vswap(engine, N, x, incx, y, incy);
+}
+template<typename FC, typename FS, class VectorLikeX, class VectorLikeY>
+void rot(gpu_engine const &engine, VectorLikeX &x, VectorLikeY &&y, FC C, FS S, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    rot(engine, N, x, incx, y, incy, C, S);
+}
+template<class VectorLikeX, class VectorLikeY, class VectorLikeP>
+void rotm(gpu_engine const &engine, VectorLikeX &x, VectorLikeY &&y, VectorLikeP const &param, int incx = 1, int incy = 1, int N = -1){
+    valid::default_size(x, incx, N);
+    rotm(engine, N, x, incx, y, incy, param);
+}
 template<class VectorLikeX> inline int iamax(gpu_engine const &engine, VectorLikeX const &x, int incx = 1, int N = -1){
     valid::default_size(x, incx, N);
     return iamax(engine, N, x, incx);

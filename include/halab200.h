@@ -97,6 +97,20 @@ int hb_scal(hb_ctx *ctx, int dtype, int n, const void *alpha, void *x, int incx)
 int hb_dot (hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, const void *y, int incy, void *result);
 int hb_nrm2(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result);
 int hb_asum(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result);   /* sum |re|+|im| (cublas?asum, gpu_blas1.hpp:124-143) */
+/* the rest of BLAS-1, so that gpu_engine carries no cuBLAS handle:
+ *   hb_swap  cublas?swap  (gpu_blas1.hpp:83-100)
+ *   hb_iamax cublasI?amax (:153-172): *result = 1-BASED index of the first entry with the largest |re| + |im| (0 when n <= 0);
+ *            the header layer subtracts 1 as the reference does
+ *   hb_rot   cublas?rot / cublasCsrot / cublasZdrot (:269-300): x' = c x + s y, y' = c y - conj(s) x; c is always of the real
+ *            type; s is of `dtype`, or of the real type when s_is_real != 0
+ *   hb_rotm  cublas{S,D}rotm (:349-371), hb_rotg cublas?rotg (:251-262), hb_rotmg cublas{S,D}rotmg (:318-341): netlib semantics;
+ *            scalar / param pointers are host or device pointers according to the pointer mode */
+int hb_swap (hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy);
+int hb_iamax(hb_ctx *ctx, int dtype, int n, const void *x, int incx, int *result);
+int hb_rot  (hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy, const void *c, const void *s, int s_is_real);
+int hb_rotm (hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy, const void *param);
+int hb_rotg (hb_ctx *ctx, int dtype, void *a, void *b, void *c, void *s);
+int hb_rotmg(hb_ctx *ctx, int dtype, void *d1, void *d2, void *x1, const void *y1, void *param);
 
 /* ---- BLAS-2 gemv, the Gram-Schmidt pair of GMRES: gpu/hala_gpu_blas2.hpp:39-62 (cublas?gemv), column-major A ---- */
 int hb_gemv(hb_ctx *ctx, int dtype, char trans, int M, int N, const void *alpha, const void *A, int lda,

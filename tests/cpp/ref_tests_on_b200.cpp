@@ -7,7 +7,8 @@
 //   tests/cuda_blas1_tests.hpp  norm2, dot, axpy, scal           (direct gpu_engine BLAS-1)
 //   tests/cuda_blas2_tests.hpp  gemv                             (direct gpu_engine gemv)
 //   tests/cuda_sparse_tests.hpp sparse_matvec                    (one-shot sparse_gemv, output resized)
-//   tests/blas1_tests.hpp       test_vcopy, test_axpy, test_rscalar, test_scal   with mixed_engine, engine + no-engine API, strides
+//   tests/blas1_tests.hpp       test_vcopy, test_vswap, test_axpy, test_rscalar, test_scal, test_iamax, test_rotate
+//                               with mixed_engine, engine + no-engine API, strides
 //   tests/sparse_tests.hpp      test_sparse_gemv                 with mixed_engine, N/T/C
 // plus solver checks written here: solve_cg / solve_gmres (reference templates, identity preconditioner) on gpu_engine and
 // mixed_engine against cpu_engine, 4 scalar types.
@@ -100,6 +101,9 @@ int main(int argc, char**){
     begin_report(std::string("shared test bodies, mixed_engine (engine API)"));
     std::vector<std::function<void(void)>> shared = {
         [&]()->void{ eng_api::test_vcopy<float, 0>(emixed); eng_api::test_vcopy<double, 0>(emixed); eng_api::test_vcopy<std::complex<float>, 0>(emixed); eng_api::test_vcopy<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_vswap<float, 0>(emixed); eng_api::test_vswap<double, 0>(emixed); eng_api::test_vswap<std::complex<float>, 0>(emixed); eng_api::test_vswap<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_iamax<float, 0>(emixed); eng_api::test_iamax<double, 0>(emixed); eng_api::test_iamax<std::complex<float>, 0>(emixed); eng_api::test_iamax<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_rotate<float, 0>(emixed); eng_api::test_rotate<double, 0>(emixed); },
         [&]()->void{ eng_api::test_axpy<float, 0>(emixed); eng_api::test_axpy<double, 0>(emixed); eng_api::test_axpy<std::complex<float>, 0>(emixed); eng_api::test_axpy<std::complex<double>, 0>(emixed); },
         [&]()->void{ eng_api::test_rscalar<float, 0>(emixed); eng_api::test_rscalar<double, 0>(emixed); eng_api::test_rscalar<std::complex<float>, 0>(emixed); eng_api::test_rscalar<std::complex<double>, 0>(emixed); },
         [&]()->void{ eng_api::test_scal<float, 0>(emixed); eng_api::test_scal<double, 0>(emixed); eng_api::test_scal<std::complex<float>, 0>(emixed); eng_api::test_scal<std::complex<double>, 0>(emixed); },
