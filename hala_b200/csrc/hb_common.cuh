@@ -153,6 +153,11 @@ template<> __device__ __forceinline__ cplx<double> ld_ro<cplx<double>>(const cpl
     double2 v = __ldg(reinterpret_cast<const double2*>(p)); return {v.x, v.y};
 }
 
+// L2-coherent load of one scalar (partials written by other blocks of the same kernel)
+template<typename T> __device__ __forceinline__ T ld_cg_T(const T *p){ return __ldcg(p); }
+template<> __device__ __forceinline__ cplx<float> ld_cg_T<cplx<float>>(const cplx<float> *p){ float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return {v.x, v.y}; }
+template<> __device__ __forceinline__ cplx<double> ld_cg_T<cplx<double>>(const cplx<double> *p){ double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return {v.x, v.y}; }
+
 // ----------------------------------------------------------------------------------------------------------------
 // reductions: warp shuffle -> shared -> one partial per block -> last block (ticket) sums the partials in
 // fixed order (deterministic; one atomic per block).

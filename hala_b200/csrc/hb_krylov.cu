@@ -5,6 +5,8 @@
 // gpu/hala_gpu_blas2.hpp:39-62) by one multi-dot pass and one multi-axpy+norm pass over the Krylov basis.
 // Every scalar these kernels consume or produce lives in device memory; nothing here synchronises with the host.
 #include "hb_common.cuh"
+#include "hb_gs_pipe.cuh"
+#include <cstdlib>
 
 static constexpr int KR_THREADS = 256;
 
@@ -189,8 +191,9 @@ __global__ void __launch_bounds__(KR_THREADS, 2) multi_dot_kernel(long long rows
                                                                   void *partials_v, unsigned int *ticket, T *h_out, const int *skip_flag){
     constexpr int KC = md_kc<T>();
     constexpr int NP = VEC ? vec16<T>::N : 1;                  // elements per packet
-    __shared__ T red[32];
+    __shared__ T wsum[KR_THREADS / 32][KC];
     if (skip_flag && *skip_flag) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *partials = reinterpret_cast<T*>(partials_v);             // layout [block][k]
     const size_t stride = (size_t) gridDim.x * blockDim.x, gtid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     const size_t npk = (size_t) rows / NP;
@@ -225,18 +228,30 @@ __global__ void __launch_bounds__(KR_THREADS, 2) multi_dot_kernel(long long rows
                 for (int j = 0; j < KC; j++) if (j < kc){ const T w = Wc[(size_t) j * ldw + i]; acc[j] = hfma(CONJ ? hconj(w) : w, ri, acc[j]); }
             }
         }
+        // one reduction for the whole chunk: shuffle every running sum down the warp, one shared slot per (warp, column),
+        // a single barrier, then KC threads add the warps' values in fixed order
         #pragma unroll
-        for (int j = 0; j < KC; j++){
-            if (j < kc){                                        // block-uniform
-                T s = block_sum(acc[j], red);
-                if (threadIdx.x == 0) partials[(size_t) blockIdx.x * k + c0 + j] = s;
-            }
+        for (int j = 0; j < KC; j++) acc[j] = warp_sum(acc[j]);
+        if (lane == 0){
+            #pragma unroll
+            for (int j = 0; j < KC; j++) wsum[warp][j] = acc[j];
         }
+        __syncthreads();
+        if (threadIdx.x < kc){
+            T s = zero_of<T>();
+            #pragma unroll
+            for (int w = 0; w < KR_THREADS / 32; w++) s = hadd(s, wsum[w][threadIdx.x]);
+            partials[(size_t) blockIdx.x * k + c0 + threadIdx.x] = s;
+        }
+        __syncthreads();
     }
     if (last_block_arrives(ticket)){
-        for (int c = 0; c < k; c++){
-            T total = sum_partials<T>(partials + c, gridDim.x, k, red);
-            if (threadIdx.x == 0) h_out[c] = total;
+        // column c is summed by warp (c mod 8): lanes stride over the blocks' partials, shuffle reduction, fixed order
+        for (int c = warp; c < k; c += KR_THREADS / 32){
+            T a = zero_of<T>();
+            for (int b = lane; b < (int) gridDim.x; b += 32) a = hadd(a, ld_cg_T(partials + (size_t) b * k + c));
+            a = warp_sum(a);
+            if (lane == 0) h_out[c] = a;
         }
     }
 }
@@ -388,6 +403,31 @@ static inline int kr_grid(const hb_ctx *ctx, long long n, int per_block){
     return (int) (need < cap ? need : cap);
 }
 
+// streaming (TMA-staged) Gram-Schmidt kernels: one wave of 2 CTAs per SM
+template<typename T, int MODE, bool CONJ>
+static int launch_gs_pipe(hb_ctx *ctx, long long rows, int k, const T *W, size_t ldw, const T *r_in, T *r_out, const T *h_dev, T scale,
+                          unsigned int *ticket, T *out, const int *skip){
+    auto kern = gs_pipe_kernel<T, MODE, CONJ>;
+    static bool configured = false;
+    if (!configured){
+        HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gs_smem_bytes<T>()));
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    const long long per16 = 16 / sizeof(T), rows_al = rows - rows % per16;
+    const long long ntiles = (rows_al + GS_R - 1) / GS_R;
+    long long grid = (long long) ctx->num_sms * 2;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    kern<<<(int) grid, GS_R, gs_smem_bytes<T>(), ctx->stream>>>(rows, rows_al, k, W, ldw, r_in, r_out, h_dev, scale, ctx->partials, ticket, out, skip);
+    return HB_OK;
+}
+static bool gs_pipe_enabled(){
+    static int on = -1;
+    if (on < 0){ const char *e = getenv("HB_GS_PIPE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 #define HB_MD_LAUNCH(CJ, VC) multi_dot_kernel<T, CJ, VC><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) r, ctx->partials, ctx->tickets + 2, hc, skip)
 int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int k, const void *W, size_t ldw, const void *r, void *h_dev, const int *skip){
     for (int c0 = 0; c0 < k; c0 += MD_KMAX){
@@ -399,8 +439,13 @@ int hb_multi_dot_internal(hb_ctx *ctx, int dtype, int conj, long long rows, int 
             // one wave of 2 CTAs per SM; a packet per thread per step
             int grid = hb_grid_for(ctx, (size_t) (rows > 0 ? rows : 1), KR_THREADS * (vec ? vec16<T>::N : 1), 2);
             const bool cj = conj && is_cplx<T>::value;
-            if (cj){ if (vec) HB_MD_LAUNCH(true, true); else HB_MD_LAUNCH(true, false); }
-            else   { if (vec) HB_MD_LAUNCH(false, true); else HB_MD_LAUNCH(false, false); }
+            if (vec && gs_pipe_enabled() && rows >= GS_R){
+                int rc = cj ? launch_gs_pipe<T, 0, true>(ctx, rows, kk, Wc, ldw, (const T*) r, nullptr, nullptr, zero_of<T>(), ctx->tickets + 2, hc, skip)
+                            : launch_gs_pipe<T, 0, false>(ctx, rows, kk, Wc, ldw, (const T*) r, nullptr, nullptr, zero_of<T>(), ctx->tickets + 2, hc, skip);
+                if (rc != HB_OK) return rc;
+            }
+            else if (cj){ if (vec) HB_MD_LAUNCH(true, true); else HB_MD_LAUNCH(true, false); }
+            else        { if (vec) HB_MD_LAUNCH(false, true); else HB_MD_LAUNCH(false, false); }
         });
         HB_LAUNCH_CHECK(ctx);
     }
@@ -417,7 +462,12 @@ int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const 
             const T *Wc = (const T*) W + (size_t) c0 * ldw;
             const bool vec = aligned16(r) && (kk == 0 || (aligned16(Wc) && (ldw * sizeof(T)) % 16 == 0));
             int grid = hb_grid_for(ctx, (size_t) (rows > 0 ? rows : 1), KR_THREADS * 2 * (vec ? vec16<T>::N : 1), 2);
-            if (vec) multi_axpy_nrm2_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) h_dev + c0,
+            if (vec && kk > 0 && gs_pipe_enabled() && rows >= GS_R){
+                int rc = launch_gs_pipe<T, 1, false>(ctx, rows, kk, Wc, ldw, (const T*) r, (T*) r, (const T*) h_dev + c0, from_real<T>((real_t<T>) scale),
+                                                     ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip);
+                if (rc != HB_OK) return rc;
+            }
+            else if (vec) multi_axpy_nrm2_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) h_dev + c0,
                         (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));
             else     multi_axpy_nrm2_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, kk, Wc, ldw, (const T*) h_dev + c0,
                         (T*) r, ctx->partials, ctx->tickets + 3, last ? (T*) nrm2sq_dev : nullptr, skip, from_real<T>((real_t<T>) scale));

@@ -181,3 +181,24 @@ def spmv_bytes(N, nnz, itemsize):
 def cg_iter_bytes(N, nnz, itemsize):
     """Algorithmic bytes of one fused CG iteration (3-kernel schedule): SURVEY.md §8(d)."""
     return nnz * (itemsize + 4) + (N + 1) * 4 + 11 * N * itemsize
+
+
+# ---------------------------------------------------------------- triangular / ILU test inputs (SURVEY.md §8 row f1)
+F1_CASES = (("lap3d27", 6), ("convdiff7", 7), ("lap2d", 13))      # (generator, size) of the recorded trsv / ILU parity cases
+
+
+def perturbed(name, n, dtype="f64", seed=77, eps=0.1):
+    """Generator `name` with a deterministic hashed perturbation of every value (makes the stencils nonsymmetric and, for the
+    complex types, genuinely complex) — the matrices the triangular-solve and ILU parity cases are built from."""
+    p, i, v = GENERATORS[name](n, dtype=dtype)
+    return p, i, (v + eps * probe_x(v.size, dtype, seed=seed)).astype(v.dtype)
+
+
+def split_triangle(pntr, indx, vals, uplo):
+    """One-triangle CSR (diagonal included) of a CSR with sorted rows: the layout the reference's cpu_triangular_matrix expects
+    (diagonal LAST in each row for 'L', FIRST for 'U'; sparse/hala_sparse_utils.hpp:283-335)."""
+    n = pntr.size - 1
+    rows = np.repeat(np.arange(n), np.diff(pntr))
+    keep = indx <= rows if uplo in "Ll" else indx >= rows
+    tp = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=n))]).astype(np.int32)
+    return tp, np.ascontiguousarray(indx[keep]), np.ascontiguousarray(vals[keep])

@@ -90,6 +90,42 @@ class _Lib:
         assert rc == 0, rc
         return res[0] if op in ("dot", "dotu", "nrm2") else yy
 
+    def trsv(self, uplo, diag, trans, pntr, indx, vals, b, alpha=1.0, general=False):
+        """x = alpha * op(T)^-1 b.  general=False: CSR holds one triangle, diagonal last (L) / first (U) — the reference's layout
+        (sparse/hala_sparse_utils.hpp:283-335); general=True (oracle only): any CSR, only the `uplo` part is used."""
+        dt = vals.dtype
+        n = pntr.size - 1
+        x = np.zeros(n, dtype=dt)
+        a = _scalar(alpha, dt)
+        bb = np.ascontiguousarray(b, dtype=dt)
+        ch = lambda c: C.c_char(c.encode())
+        if self.prefix == "orc_":
+            rc = self._f("trsv")(CODE[dt], int(bool(general)), ch(uplo), ch(diag), ch(trans), n, _ptr(a), _ptr(pntr), _ptr(indx), _ptr(vals), _ptr(bb), _ptr(x))
+        else:
+            assert not general, "the reference's cpu_triangular_matrix expects a one-triangle CSR"
+            rc = self._f("trsv")(CODE[dt], ch(uplo), ch(diag), ch(trans), n, _ptr(a), int(indx.size), _ptr(pntr), _ptr(indx), _ptr(vals), _ptr(bb), _ptr(x))
+        assert rc == 0, rc
+        return x
+
+    def ilu(self, pntr, indx, vals, x):
+        """ILU(0) factors in the pattern of the matrix (sorted rows, diagonal present) and U^-1 L^-1 x
+        (sparse/hala_sparse_utils.hpp:228-274). Returns (factors, applied)."""
+        dt = vals.dtype
+        n = pntr.size - 1
+        fac = np.zeros(indx.size, dtype=dt)
+        xx = np.ascontiguousarray(x, dtype=dt)
+        if self.prefix == "orc_":
+            diag = np.zeros(n, dtype=np.int32)
+            rc = self._f("ilu_factor")(CODE[dt], n, _ptr(pntr), _ptr(indx), _ptr(vals), _ptr(diag), _ptr(fac))
+            assert rc == 0, rc
+            r = xx.copy()
+            rc = self._f("ilu_apply")(CODE[dt], n, _ptr(pntr), _ptr(indx), _ptr(diag), _ptr(fac), _ptr(r))
+        else:
+            r = np.zeros(n, dtype=dt)
+            rc = self._f("ilu")(CODE[dt], n, int(indx.size), _ptr(pntr), _ptr(indx), _ptr(vals), _ptr(fac), _ptr(xx), _ptr(r))
+        assert rc == 0, rc
+        return fac, r
+
     def gemv(self, trans, M, N, A, x, alpha=1.0, beta=0.0, y=None, lda=None):
         dt = A.dtype
         lda = M if lda is None else lda

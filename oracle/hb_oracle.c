@@ -2,7 +2,8 @@
  *
  * A plain-C, single-threaded restatement of what LIBHALA/hala's cpu_engine path computes for
  *   CSR SpMV (sparse/hala_sparse_utils.hpp:103-118), BLAS-1 (blas/hala_blas_1.hpp), the Gram-Schmidt
- *   gemv pair, CG (hex/solvers/hala_solvers_cg.hpp:92-156,181-227) and GMRES (hala_solvers_gmres.hpp:127-230).
+ *   gemv pair, CG (hex/solvers/hala_solvers_cg.hpp:92-156,181-227) and GMRES (hala_solvers_gmres.hpp:127-230),
+ *   and the sparse triangular solve and ILU(0) (sparse/hala_sparse_utils.hpp:228-335).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load liboracle.so, and only
  * as the checker. The product (libhalab200.so) never links or calls it.
  *
@@ -162,6 +163,28 @@ int orc_gemv(int dtype, char trans, int M, int N, const void *alpha, const void 
        gemv_d(trans, M, N, *(const double*) alpha, A, lda, x, *(const double*) beta, y),
        gemv_c(trans, M, N, *(const float _Complex*) alpha, A, lda, x, *(const float _Complex*) beta, y),
        gemv_z(trans, M, N, *(const double _Complex*) alpha, A, lda, x, *(const double _Complex*) beta, y))
+    return 0;
+}
+
+/* general != 0: any CSR, only the uplo triangle is used (cuSPARSE fill-mode semantics); general == 0: the reference's layout
+ * (one triangle, diagonal last / first) */
+int orc_trsv(int dtype, int general, char uplo, char diag, char trans, int n, const void *alpha, const int *pntr, const int *indx,
+             const void *vals, const void *b, void *x){
+#define TR(sfx, TT) if (general) trsv_general_##sfx(uplo, diag, trans, n, *(const TT*) alpha, pntr, indx, vals, b, x); \
+                    else trsv_##sfx(uplo, diag, trans, n, *(const TT*) alpha, pntr, indx, vals, b, x)
+    SW(dtype, TR(s, float), TR(d, double), TR(c, float _Complex), TR(z, double _Complex))
+    return 0;
+}
+/* ilu = ILU(0) factors in the pattern of the matrix; diag = position of each row's diagonal. Returns 3 when a diagonal is missing. */
+int orc_ilu_factor(int dtype, int n, const int *pntr, const int *indx, const void *vals, int *diag, void *ilu){
+    int rc = 0;
+    SW(dtype, rc = ilu_factor_s(n, pntr, indx, vals, diag, ilu), rc = ilu_factor_d(n, pntr, indx, vals, diag, ilu),
+              rc = ilu_factor_c(n, pntr, indx, vals, diag, ilu), rc = ilu_factor_z(n, pntr, indx, vals, diag, ilu))
+    return rc ? 3 : 0;
+}
+int orc_ilu_apply(int dtype, int n, const int *pntr, const int *indx, const int *diag, const void *ilu, void *x){
+    SW(dtype, ilu_apply_s(n, pntr, indx, diag, ilu, x), ilu_apply_d(n, pntr, indx, diag, ilu, x),
+              ilu_apply_c(n, pntr, indx, diag, ilu, x), ilu_apply_z(n, pntr, indx, diag, ilu, x))
     return 0;
 }
 

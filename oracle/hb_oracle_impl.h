@@ -232,3 +232,115 @@ static int NAME(gmres)(int n, const int *pntr, const int *indx, const T *vals, c
     free(t); free(r); free(W); free(H); free(S); free(Z); free(C); free(coeffs);
     return total;
 }
+
+/* sparse/hala_sparse_utils.hpp:283-335  sparse_trsv_array<diag,T>: x = alpha * op(T)^-1 b for a CSR that holds exactly
+ * one triangle with sorted rows — the diagonal entry is the LAST of its row for uplo 'L' and the FIRST for uplo 'U'
+ * (stored, and skipped, even when diag == 'U').  'N' walks the rows (forward for L, backward for U) with a left-to-right
+ * sum; 'T'/'C' zero x and scatter column-wise in the opposite row order. */
+static void NAME(trsv)(char uplo, char diag, char trans, int n, T alpha, const int *pntr, const int *indx, const T *vals,
+                       const T *b, T *x){
+    const int unit = (diag == 'U' || diag == 'u'), lower = (uplo == 'L' || uplo == 'l');
+    if (n <= 0) return;
+    if (trans == 'N' || trans == 'n'){
+        if (lower){
+            x[0] = unit ? alpha * b[0] : alpha * b[0] / vals[0];
+            for(int i=1; i<n; i++){
+                T s = 0;
+                for(int j=pntr[i]; j<pntr[i+1]-1; j++) s += vals[j] * x[indx[j]];
+                x[i] = unit ? (alpha * b[i] - s) : (alpha * b[i] - s) / vals[pntr[i+1]-1];
+            }
+        }else{
+            x[n-1] = unit ? alpha * b[n-1] : alpha * b[n-1] / vals[pntr[n]-1];
+            for(int i=n-2; i>=0; i--){
+                T s = 0;
+                for(int j=pntr[i]+1; j<pntr[i+1]; j++) s += vals[j] * x[indx[j]];
+                x[i] = unit ? (alpha * b[i] - s) : (alpha * b[i] - s) / vals[pntr[i]];
+            }
+        }
+    }else{
+        const int cj = (trans == 'C' || trans == 'c');
+        for(int i=0; i<n; i++) x[i] = 0;
+        if (lower){
+            for(int i=n-1; i>=0; i--){
+                T d = vals[pntr[i+1]-1];
+                x[i] = unit ? (alpha * b[i] - x[i]) : (alpha * b[i] - x[i]) / (cj ? CONJ(d) : d);
+                for(int j=pntr[i]; j<pntr[i+1]-1; j++) x[indx[j]] += x[i] * (cj ? CONJ(vals[j]) : vals[j]);
+            }
+        }else{
+            for(int i=0; i<n; i++){
+                T d = vals[pntr[i]];
+                x[i] = unit ? (alpha * b[i] - x[i]) : (alpha * b[i] - x[i]) / (cj ? CONJ(d) : d);
+                for(int j=pntr[i]+1; j<pntr[i+1]; j++) x[indx[j]] += x[i] * (cj ? CONJ(vals[j]) : vals[j]);
+            }
+        }
+    }
+}
+
+/* The same solve on a GENERAL CSR of which only the `uplo` triangle is used (entries on the other side are skipped, the
+ * diagonal is looked up by column index; diag 'U' ignores a stored diagonal) — the cuSPARSE fill-mode semantics that
+ * gpu_ilu relies on when it hands the full ILU array to both triangular matrices (gpu/hala_gpu_ilu.hpp:88-89).  For a
+ * one-triangle CSR this performs exactly the operations of NAME(trsv) in the same order. */
+static void NAME(trsv_general)(char uplo, char diag, char trans, int n, T alpha, const int *pntr, const int *indx, const T *vals,
+                               const T *b, T *x){
+    const int unit = (diag == 'U' || diag == 'u'), lower = (uplo == 'L' || uplo == 'l');
+    const int nt = (trans == 'N' || trans == 'n'), cj = (trans == 'C' || trans == 'c');
+    if (!nt) for(int i=0; i<n; i++) x[i] = 0;
+    /* 'N' on L and 'T' on U run forward; 'N' on U and 'T' on L run backward */
+    const int forward = (nt == lower);
+    for(int step=0; step<n; step++){
+        const int i = forward ? step : n - 1 - step;
+        T d = 1, s = 0;
+        for(int j=pntr[i]; j<pntr[i+1]; j++){
+            const int c = indx[j];
+            if (c == i){ if (!unit) d = vals[j]; }
+            else if (nt && (lower ? c < i : c > i)) s += vals[j] * x[c];
+        }
+        if (nt) x[i] = unit ? (alpha * b[i] - s) : (alpha * b[i] - s) / d;
+        else{
+            x[i] = unit ? (alpha * b[i] - x[i]) : (alpha * b[i] - x[i]) / (cj ? CONJ(d) : d);
+            for(int j=pntr[i]; j<pntr[i+1]; j++){
+                const int c = indx[j];
+                if (lower ? c < i : c > i) x[c] += x[i] * (cj ? CONJ(vals[j]) : vals[j]);
+            }
+        }
+    }
+}
+
+/* sparse/hala_sparse_utils.hpp:228-253 factorize_ilu_array (after get_diagonal_index and a copy of the values): right-looking
+ * ILU(0) on sorted rows with the diagonal present.  Returns 0, or 1 + row when a row has no diagonal entry. */
+static int NAME(ilu_factor)(int n, const int *pntr, const int *indx, const T *vals, int *diag, T *ilu){
+    for(int i=0; i<n; i++){
+        int j = pntr[i];
+        while (j < pntr[i+1] && indx[j] < i) j++;
+        if (j == pntr[i+1] || indx[j] != i) return 1 + i;
+        diag[i] = j;
+    }
+    for(int j=0; j<pntr[n]; j++) ilu[j] = vals[j];
+    for(int i=0; i<n; i++){
+        T u = ilu[diag[i]];
+        for(int j=i+1; j<n; j++){
+            int jc = pntr[j];
+            while (indx[jc] < i) jc++;          /* the diagonal (column j > i) stops the scan */
+            if (indx[jc] == i){
+                ilu[jc] /= u;
+                T l = ilu[jc];
+                int ik = diag[i] + 1, jk = jc + 1;
+                while (ik < pntr[i+1] && jk < pntr[j+1]){
+                    if (indx[ik] == indx[jk]){ ilu[jk] -= l * ilu[ik]; ik++; jk++; }
+                    else if (indx[ik] < indx[jk]) ik++;
+                    else jk++;
+                }
+            }
+        }
+    }
+    return 0;
+}
+/* sparse/hala_sparse_utils.hpp:261-274 apply_ilu_array: x <- U^-1 L^-1 x (unit lower, stored diagonal upper), in place */
+static void NAME(ilu_apply)(int n, const int *pntr, const int *indx, const int *diag, const T *ilu, T *x){
+    for(int i=1; i<n; i++)
+        for(int j=pntr[i]; j<diag[i]; j++) x[i] -= ilu[j] * x[indx[j]];
+    for(int i=n-1; i>=0; i--){
+        for(int j=diag[i]+1; j<pntr[i+1]; j++) x[i] -= ilu[j] * x[indx[j]];
+        x[i] /= ilu[diag[i]];
+    }
+}

@@ -11,6 +11,8 @@
 //   ref_gemv                                              blas/hala_blas_2.hpp (gemv) — the Gram-Schmidt pair of hex/solvers/hala_solvers_gmres.hpp:47-50
 //   ref_cg     -> hala::solve_cg(cpu_engine, ...)         hex/solvers/hala_solvers_cg.hpp:232-246 -> :181-227 -> solve_cg_core :92-156
 //   ref_gmres  -> hala::solve_gmres(cpu_engine, ...)      hex/solvers/hala_solvers_gmres.hpp:127-230
+//   ref_trsv   -> hala::sparse_trsv(cpu_triangular_matrix) sparse/hala_sparse_structs.hpp:257-269 -> sparse_trsv_array (hala_sparse_utils.hpp:283-335)
+//   ref_ilu    -> factorize_ilu + make_ilu(cpu_engine).apply sparse/hala_sparse_ilu.hpp -> hala_sparse_utils.hpp:228-274
 // The preconditioner is the identity lambda SURVEY.md §8(d) prescribes: hala::vcopy(engine, in, out).
 //
 // The same source is compiled twice: once against the stock headers (libhala_ref.so) and once with
@@ -117,6 +119,36 @@ int gemv(char trans, int M, int N, const void *alpha, const void *A, int lda, co
     return 0;
 }
 
+// sparse_trsv through cpu_triangular_matrix (sparse/hala_sparse_structs.hpp:257-269 -> sparse_trsv_array, hala_sparse_utils.hpp:283-335)
+template<typename T>
+int trsv(char uplo, char diag, char trans, int n, const void *alpha, int nnz, const int *pntr, const int *indx, const void *vals,
+         const void *b, void *x){
+    hala::cpu_engine e;
+    view<const int> vp(pntr, (size_t) n + 1), vi(indx, (size_t) nnz);
+    view<const T> vv((T const*) vals, (size_t) nnz), vb((T const*) b, (size_t) n);
+    view<T> vx((T*) x, (size_t) n);
+    auto tri = hala::make_triangular_matrix(e, uplo, diag, vp, vi, vv);
+    hala::sparse_trsv(trans, tri, rd<T>(alpha), vb, vx);
+    return 0;
+}
+// make_ilu(cpu_engine) + apply (sparse/hala_sparse_ilu.hpp -> factorize_ilu_array / apply_ilu_array, hala_sparse_utils.hpp:228-274);
+// also returns the factors themselves through factorize_ilu
+template<typename T>
+int ilu(int n, int nnz, const int *pntr, const int *indx, const void *vals, void *ilu_out, const void *x, void *r){
+    hala::cpu_engine e;
+    view<const int> vp(pntr, (size_t) n + 1), vi(indx, (size_t) nnz);
+    view<const T> vv((T const*) vals, (size_t) nnz), vx((T const*) x, (size_t) n);
+    view<T> vr((T*) r, (size_t) n);
+    std::vector<int> diag;
+    std::vector<T> factors;
+    hala::get_diagonal_index(vp, vi, diag);
+    hala::factorize_ilu(vp, vi, vv, diag, factors);
+    std::memcpy(ilu_out, factors.data(), sizeof(T) * (size_t) nnz);
+    auto pre = hala::make_ilu(e, vp, vi, vv, 'N');
+    pre.apply(vx, vr);
+    return 0;
+}
+
 #define DISPATCH(dtype, call) \
     switch(dtype){ \
         case 0: { using T = float; return call; } \
@@ -148,6 +180,13 @@ int RNAME(blas1)(int dtype, int op, int n, const void *alpha, const void *x, int
 int RNAME(gemv)(int dtype, char trans, int M, int N, const void *alpha, const void *A, int lda, const void *x,
                 const void *beta, void *y){
     try{ DISPATCH(dtype, gemv<T>(trans, M, N, alpha, A, lda, x, beta, y)) }catch(...){ return 3; }
+}
+int RNAME(trsv)(int dtype, char uplo, char diag, char trans, int n, const void *alpha, int nnz, const int *pntr, const int *indx,
+                const void *vals, const void *b, void *x){
+    try{ DISPATCH(dtype, trsv<T>(uplo, diag, trans, n, alpha, nnz, pntr, indx, vals, b, x)) }catch(...){ return 3; }
+}
+int RNAME(ilu)(int dtype, int n, int nnz, const int *pntr, const int *indx, const void *vals, void *ilu_out, const void *x, void *r){
+    try{ DISPATCH(dtype, ilu<T>(n, nnz, pntr, indx, vals, ilu_out, x, r)) }catch(...){ return 3; }
 }
 const char* RNAME(version)(){ return "LIBHALA/hala " HALA_VERSION_STRING " cpu_engine"; }
 

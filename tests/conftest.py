@@ -21,6 +21,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_f1():
+    """Triangular-solve / ILU(0) outputs of the unmodified reference (tests/golden/make_golden.py f1)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs_f1.npz"))
+
+
+@pytest.fixture(scope="session")
 def ref_tests():
     """Vectors harvested from the reference's own tests (file:line inside the JSON)."""
     with open(os.path.join(ROOT, "tests", "golden", "ref_tests.json")) as f:

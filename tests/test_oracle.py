@@ -184,3 +184,50 @@ def test_generators_are_well_formed():
         assert np.all(np.diff(cols) > 0) and r in cols
     A = dense_from_csr(*mg.powerlaw(N=300, lmax=64), 300)
     assert np.all(np.abs(np.diag(A)) > np.sum(np.abs(A), axis=1) - np.abs(np.diag(A)))
+
+
+# ---------------------------------------------------------------- triangular solves and ILU(0)
+F1_TOL = {"f32": 2e-4, "f64": 1e-11, "c32": 2e-4, "c64": 1e-11}
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_oracle_trsv_ilu_match_recorded_reference(orc, golden_f1, dt):
+    for name, n in mg.F1_CASES:
+        p, i, v = mg.perturbed(name, n, dt)
+        b = mg.probe_x(p.size - 1, dt, seed=31)
+        for uplo in "LU":
+            tp, ti, tv = mg.split_triangle(p, i, v, uplo)
+            for diag in "NU":
+                for tr in "NTC":
+                    want = golden_f1[f"trsv/{name}:{n}/{dt}/{uplo}{diag}{tr}"]
+                    scale = np.abs(want).max()
+                    got = orc.trsv(uplo, diag, tr, tp, ti, tv, b, alpha=0.5)
+                    assert np.abs(got - want).max() <= F1_TOL[dt] * scale, (name, uplo, diag, tr)
+                    # the general-CSR form (cuSPARSE fill-mode semantics, what gpu_ilu relies on) on the FULL matrix
+                    got = orc.trsv(uplo, diag, tr, p, i, v, b, alpha=0.5, general=True)
+                    assert np.abs(got - want).max() <= F1_TOL[dt] * scale, (name, uplo, diag, tr, "general")
+        fac, r = orc.ilu(p, i, v, b)
+        assert np.abs(fac - golden_f1[f"ilu/{name}:{n}/{dt}/factors"]).max() <= F1_TOL[dt] * np.abs(fac).max()
+        want = golden_f1[f"ilu/{name}:{n}/{dt}/apply"]
+        assert np.abs(r - want).max() <= F1_TOL[dt] * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_oracle_trsv_ilu_reference_test_vectors(orc, dt):
+    """tests/sparse_tests.hpp:259-311 (trsv: X = 0.5 * op(T)^-1 (2 op(A) Xref) == Xref) and :423-440 (ilu)"""
+    t = NP[dt]
+    A = np.array([[1, 0, 0], [4, 2, 0], [5, 0, 3]], dtype=t)
+    xref = mg.probe_x(3, dt, seed=4)
+    pl, il, vl = np.array([0, 1, 3, 5], np.int32), np.array([0, 0, 1, 0, 2], np.int32), np.array([1, 4, 2, 5, 3], dtype=t)
+    for tr, op in (("N", A), ("T", A.T), ("C", A.conj().T)):
+        np.testing.assert_allclose(orc.trsv("L", "N", tr, pl, il, vl, 2 * op @ xref, alpha=0.5), xref, rtol=1e-5 if "32" in dt else 1e-13)
+    Au = np.array([[1, 0, 0], [1, 1, 0], [2, 0, 1]], dtype=t)
+    vu = np.array([2, 1, 3, 2, 4], dtype=t)
+    np.testing.assert_allclose(orc.trsv("L", "U", "N", pl, il, vu, 2 * Au @ xref, alpha=0.5), xref, rtol=1e-5 if "32" in dt else 1e-13)
+    pu, iu, vv = np.array([0, 3, 4, 5], np.int32), np.array([0, 1, 2, 1, 2], np.int32), np.array([1, 4, 5, 2, 3], dtype=t)
+    np.testing.assert_allclose(orc.trsv("U", "N", "N", pu, iu, vv, 2 * A.T @ xref, alpha=0.5), xref, rtol=1e-5 if "32" in dt else 1e-13)
+    np.testing.assert_allclose(orc.trsv("U", "N", "T", pu, iu, vv, 2 * A @ xref, alpha=0.5), xref, rtol=1e-5 if "32" in dt else 1e-13)
+    p, i = np.array([0, 3, 6, 9], np.int32), np.array([0, 1, 2, 0, 1, 2, 0, 1, 2], np.int32)
+    fac, r = orc.ilu(p, i, np.array([3, 2, 1, 2, 4, 3, 2, 1, 6], dtype=t), np.array([1, 2, 3], dtype=t))
+    np.testing.assert_allclose(fac, [3, 2, 1, 2 / 3, 8 / 3, 7 / 3, 2 / 3, -0.125, 5.625], rtol=1e-5 if "32" in dt else 1e-13)
+    np.testing.assert_allclose(r, [1 / 9, 1 / 9, 4 / 9], rtol=1e-5 if "32" in dt else 1e-13)
