@@ -56,6 +56,12 @@ SIGNATURES = {
     "hb_spmv": (_i, [_vp, _vp, C.c_char, _vp, _vp, _vp, _vp]),
     "hb_spmv_dot": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hb_csr_set_variant": (_i, [_vp, _i]),
+    "hb_tri_create": (_i, [_vp, _i, C.c_char, C.c_char, _i, _i, _vp, _vp, _vp, _pvp]),
+    "hb_tri_destroy": (_i, [_vp]),
+    "hb_tri_info": (_i, [_vp, _pi, _pi, _pi]),
+    "hb_sptrsv": (_i, [_vp, _vp, C.c_char, _vp, _vp, _i, _vp, _i]),
+    "hb_sptrsm": (_i, [_vp, _vp, C.c_char, C.c_char, _i, _vp, _vp, _i]),
+    "hb_ilu0": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hb_copy": (_i, [_vp, _i, _i, _vp, _i, _vp, _i]),
     "hb_axpy": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i]),
     "hb_scal": (_i, [_vp, _i, _i, _vp, _vp, _i]),

@@ -30,7 +30,8 @@ extern "C" {
 #endif
 
 typedef struct hb_ctx hb_ctx;   /* replaces the cuBLAS+cuSPARSE handle pair held by gpu_engine (gpu/hala_gpu_engine.hpp:47-163) */
-typedef struct hb_csr hb_csr;   /* replaces cusparseSpMatDescr_t + cached buffer sizes of gpu_sparse_matrix (gpu/hala_cuda_sparse_general.hpp:191-375) */
+typedef struct hb_csr hb_csr;
+typedef struct hb_tri hb_tri;   /* replaces cusparseSpMatDescr_t + the cached SpSV/SpSM analyses of gpu_triangular_matrix (gpu/hala_cuda_sparse_triangular.hpp:38-110) */   /* replaces cusparseSpMatDescr_t + cached buffer sizes of gpu_sparse_matrix (gpu/hala_cuda_sparse_general.hpp:191-375) */
 
 enum { HB_F32 = 0, HB_F64 = 1, HB_C32 = 2, HB_C64 = 3 };
 enum { HB_OK = 0, HB_ERR_CUDA = 1, HB_ERR_ARG = 2, HB_ERR_ALLOC = 3, HB_ERR_UNSUPPORTED = 4, HB_ERR_NCCL = 5, HB_ERR_NOT_CONVERGED = 6 };
@@ -89,6 +90,24 @@ int hb_spmv_dot(hb_ctx *ctx, const hb_csr *csr, const void *x, void *y, void *do
 /* selects the SpMV kernel variant for op 'N': 0 = auto, 1 = row-vector (sub-warp per row), 2 = staged tiles (LDG),
  * 3 = staged tiles (TMA bulk copy pipeline).  For benchmarking; auto is what the header layer uses. */
 int hb_csr_set_variant(hb_csr *csr, int variant);
+
+/* ---- sparse triangular solves and ILU(0): gpu_triangular_matrix (gpu/hala_cuda_sparse_triangular.hpp:38-454 ->
+ *      cusparseSpSV / cusparseSpSM) and gpu_ilu (gpu/hala_gpu_ilu.hpp:45-199 -> cusparse?csrilu02 + two triangular solves) ----
+ * hb_tri_create : non-owning view of a CSR of which only the `uplo` ('L'/'U') triangle is used — the CSR may hold the whole
+ *   matrix, as gpu_ilu passes it (gpu_ilu.hpp:88-89); diag 'U' = unit diagonal (a stored diagonal is ignored), 'N' = stored.
+ *   The dependency analysis is done on first use per direction and cached; values are read at solve time.
+ * hb_sptrsv : x = alpha * op(T)^-1 b, op = N / T / C (gpu_triangular_matrix::trsv -> cusparseSpSV_solve); b, x may alias (same stride)
+ * hb_sptrsm : the same in place on nrhs right-hand sides: transb 'N' -> B is rows x nrhs column-major; 'T'/'C' -> B is nrhs x rows and
+ *   every row is a right-hand side (gpu_triangular_matrix::trsm -> cusparseSpSM_solve)
+ * hb_ilu0   : ILU(0) factors of a CSR with sorted rows and a full diagonal, in the pattern of the matrix (unit-lower L below the
+ *   diagonal, U on and above it); `ilu` may alias `vals`; HB_ERR_ARG when a row lacks its diagonal (cusparse?csrilu02) */
+int hb_tri_create(hb_ctx *ctx, int dtype, char uplo, char diag, int rows, int nnz,
+                  const int *pntr, const int *indx, const void *vals, hb_tri **tri);
+int hb_tri_destroy(hb_tri *tri);
+int hb_tri_info(const hb_tri *tri, int *rows, int *nnz, int *nlevels);     /* nlevels: dependency levels of op 'N' (0 before its first solve) */
+int hb_sptrsv(hb_ctx *ctx, hb_tri *tri, char trans, const void *alpha, const void *b, int incb, void *x, int incx);
+int hb_sptrsm(hb_ctx *ctx, hb_tri *tri, char transa, char transb, int nrhs, const void *alpha, void *B, int ldb);
+int hb_ilu0(hb_ctx *ctx, int dtype, int rows, int nnz, const int *pntr, const int *indx, const void *vals, void *ilu);
 
 /* ---- BLAS-1: gpu/hala_gpu_blas1.hpp  vcopy :48-65, norm2 :102-121, dot<conj> :178-198, axpy :204-222, scal :228-245 ---- */
 int hb_copy(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *y, int incy);
