@@ -308,14 +308,15 @@ template<typename T>
 int solve_typed(hb_ctx *ctx, hb_tri *t, char trans, scalar_arg<T> alpha, const T *b, long long incb, T *x, long long incx){
     const int n = t->rows;
     int rc;
-    HB_CUDA(cudaMemsetAsync(t->ticket, 0, sizeof(unsigned int), ctx->stream));
     if (hb_is_n(trans)){
         if ((rc = ensure_n_analysis(t)) != HB_OK) return rc;
+        HB_CUDA(cudaMemsetAsync(t->ticket, 0, sizeof(unsigned int), ctx->stream));      // after the analysis: it uses the same dispenser
         t->epoch++;
         tri_solve_n_kernel<T><<<t->grid, TS_THREADS, 0, ctx->stream>>>(n, t->lower ? 1 : 0, t->unit ? 1 : 0, t->pntr, t->indx, (const T*) t->vals, t->order,
                                                                        alpha, b, incb, x, incx, t->done, t->epoch, t->ticket);
     }else{
         if ((rc = ensure_t_analysis(t)) != HB_OK) return rc;
+        HB_CUDA(cudaMemsetAsync(t->ticket, 0, sizeof(unsigned int), ctx->stream));
         HB_CUDA(cudaMemcpyAsync(t->cnt, t->cnt0, sizeof(int) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
         HB_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(T) * (size_t) n, ctx->stream));
         if (hb_is_c(trans) && is_cplx<T>::value)

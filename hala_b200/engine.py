@@ -304,6 +304,100 @@ class gpu_sparse_matrix:
         check(lib.hb_spmv(self.engine.ctx, self.h, trans.encode(), _host_ptr(a), _dptr(x), _host_ptr(b), _dptr(y)), "hb_spmv")
 
 
+# ---------------------------------------------------------------- triangular solves / ILU(0) (gpu/hala_cuda_sparse_triangular.hpp, gpu/hala_gpu_ilu.hpp)
+class gpu_triangular_matrix:
+    """Non-owning view of a CSR of which only the `uplo` triangle is used (reference :38-110); analysis cached per direction."""
+
+    def __init__(self, engine, uplo, diag, pntr, indx, vals, policy="N"):
+        self.engine, self.uplo, self.diag = engine, uplo, diag
+        self.dtype = vals.dtype
+        self.nrows, self.nz = pntr.size() - 1, indx.size()
+        self._keep = (pntr, indx, vals)
+        self.h = C.c_void_p()
+        check(lib.hb_tri_create(engine.ctx, _CODE[vals.dtype], uplo.encode(), diag.encode(), self.nrows, self.nz, pntr.ptr, indx.ptr, vals.ptr,
+                                C.byref(self.h)), "hb_tri_create")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.hb_tri_destroy(self.h)
+        except Exception:
+            pass
+
+    def rows(self):
+        return self.nrows
+
+    def nnz(self):
+        return self.nz
+
+    def levels(self):
+        m = C.c_int(0)
+        check(lib.hb_tri_info(self.h, None, None, C.byref(m)), "hb_tri_info")
+        return m.value
+
+    def trsv_buffer_size(self, *a):
+        return 0
+
+    def trsv(self, trans, alpha, b, x, work=None):
+        if x.size() != self.nrows:
+            x.resize(self.nrows)                # pure output is resized (check_set_size, reference :418)
+        a = _sc(alpha, self.dtype)
+        check(lib.hb_sptrsv(self.engine.ctx, self.h, trans.encode(), _host_ptr(a), b.ptr, 1, x.ptr, 1), "hb_sptrsv")
+
+    def trsm(self, transa, transb, nrhs, alpha, B, ldb=-1, work=None):
+        if ldb < 0:
+            ldb = self.nrows if transb in "Nn" else nrhs
+        a = _sc(alpha, self.dtype)
+        check(lib.hb_sptrsm(self.engine.ctx, self.h, transa.encode(), transb.encode(), nrhs, _host_ptr(a), B.ptr, ldb), "hb_sptrsm")
+
+
+def make_triangular_matrix(engine, uplo, diag, pntr, indx, vals, policy="N"):
+    return gpu_triangular_matrix(engine, uplo, diag, pntr, indx, vals, policy)
+
+
+def sparse_trsv(trans, tri, alpha, b, x):
+    tri.trsv(trans, alpha, b, x)
+
+
+def sparse_trsm(transa, transb, nrhs, tri, alpha, B, ldb=-1):
+    tri.trsm(transa, transb, nrhs, alpha, B, ldb)
+
+
+class gpu_ilu:
+    """ILU(0) preconditioner (reference gpu/hala_gpu_ilu.hpp:45-199): factors in the pattern of the matrix, applied as a unit-lower
+    solve followed by an upper solve on the same array."""
+
+    def __init__(self, engine, pntr, indx, vals, policy="N"):
+        self.engine, self.dtype = engine, vals.dtype
+        self.num_rows, self.nnz = pntr.size() - 1, indx.size()
+        self.ilu = gpu_vector(engine, vals.dtype, self.nnz)
+        check(lib.hb_ilu0(engine.ctx, _CODE[vals.dtype], self.num_rows, self.nnz, pntr.ptr, indx.ptr, vals.ptr, self.ilu.ptr), "hb_ilu0")
+        self.upper = gpu_triangular_matrix(engine, "U", "N", pntr, indx, self.ilu, policy)
+        self.lower = gpu_triangular_matrix(engine, "L", "U", pntr, indx, self.ilu, policy)
+        self._tmp = gpu_vector(engine, vals.dtype, self.num_rows)
+
+    def factors(self):
+        return self.ilu.unload()
+
+    def buffer_size(self, *a):
+        return 0
+
+    def apply(self, x, r, num_rhs=1, work=None):
+        if r.size() != num_rhs * self.num_rows:
+            r.resize(num_rhs * self.num_rows)
+        if num_rhs == 1:
+            self.lower.trsv("N", 1.0, x, self._tmp)
+            self.upper.trsv("N", 1.0, self._tmp, r)
+        else:
+            vcopy(self.engine, x, r)
+            self.lower.trsm("N", "N", num_rhs, 1.0, r, self.num_rows)
+            self.upper.trsm("N", "N", num_rhs, 1.0, r, self.num_rows)
+
+
+def make_ilu(engine, pntr, indx, vals, policy="N"):
+    return gpu_ilu(engine, pntr, indx, vals, policy)
+
+
 def make_sparse_matrix(engine, *args):
     """make_sparse_matrix(engine, [rows,] cols, [nnz,] pntr, indx, vals) — gpu/hala_cuda_sparse_general.hpp:382-401."""
     if len(args) == 6:

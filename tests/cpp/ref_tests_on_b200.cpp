@@ -9,13 +9,15 @@
 //   tests/cuda_sparse_tests.hpp sparse_matvec                    (one-shot sparse_gemv, output resized)
 //   tests/blas1_tests.hpp       test_vcopy, test_vswap, test_axpy, test_rscalar, test_scal, test_iamax, test_rotate
 //                               with mixed_engine, engine + no-engine API, strides
-//   tests/sparse_tests.hpp      test_sparse_gemv                 with mixed_engine, N/T/C
+//   tests/sparse_tests.hpp      test_sparse_gemv, test_sparse_trsv, test_sparse_trsm   with mixed_engine, N/T/C
+//   tests/solvers_tests.hpp     test_cg, test_gmres              the reference's ILU-preconditioned solver tests, mixed_engine
 // plus solver checks written here: solve_cg / solve_gmres (reference templates, identity preconditioner) on gpu_engine and
 // mixed_engine against cpu_engine, 4 scalar types.
 #include "cuda_core_tests.hpp"
 #include "cuda_blas1_tests.hpp"
 #include "cuda_blas2_tests.hpp"
 #include "cuda_sparse_tests.hpp"
+#include "solvers_tests.hpp"
 
 namespace eng_api {      // the "engine as first argument" flavour of the shared test bodies
 #undef mengine
@@ -110,6 +112,15 @@ int main(int argc, char**){
         [&]()->void{ eng_api::test_sparse_gemv<float, 0>(emixed); eng_api::test_sparse_gemv<double, 0>(emixed); eng_api::test_sparse_gemv<std::complex<float>, 0>(emixed); eng_api::test_sparse_gemv<std::complex<double>, 0>(emixed); },
     };
     for(auto const &t : shared) perform(t);
+
+    begin_report(std::string("triangular solves and ILU-preconditioned solvers (reference tests, mixed_engine)"));
+    std::vector<std::function<void(void)>> f1 = {
+        [&]()->void{ eng_api::test_sparse_trsv<float, 0>(emixed); eng_api::test_sparse_trsv<double, 0>(emixed); eng_api::test_sparse_trsv<std::complex<float>, 0>(emixed); eng_api::test_sparse_trsv<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_sparse_trsm<float, 0>(emixed); eng_api::test_sparse_trsm<double, 0>(emixed); eng_api::test_sparse_trsm<std::complex<float>, 0>(emixed); eng_api::test_sparse_trsm<std::complex<double>, 0>(emixed); },
+        [&]()->void{ test_cg<float>(emixed); test_cg<double>(emixed); test_cg<std::complex<float>>(emixed); test_cg<std::complex<double>>(emixed); },
+        [&]()->void{ test_gmres<float>(emixed); test_gmres<double>(emixed); test_gmres<std::complex<float>>(emixed); test_gmres<std::complex<double>>(emixed); },
+    };
+    for(auto const &t : f1) perform(t);
 
     begin_report(std::string("reference solver templates on gpu_engine / mixed_engine"));
     perform([]()->void{ solvers_on_engines<float>(); solvers_on_engines<double>(); solvers_on_engines<std::complex<float>>(); solvers_on_engines<std::complex<double>>(); });
