@@ -8,5 +8,5 @@ from . import matgen  # noqa: F401  (numpy only)
 from .capi import HalaB200Error, LIB_PATH  # noqa: F401
 from .engine import (gpu_device_count, gpu_engine, gpu_vector, gpu_sparse_matrix, make_sparse_matrix,  # noqa: F401
                      gpu_triangular_matrix, make_triangular_matrix, sparse_trsv, sparse_trsm, gpu_ilu, make_ilu,
-                     vcopy, axpy, scal, dot, dotu, norm2, asum, vswap, iamax, rot, rotg, rotm, rotmg, gemv, sparse_gemv,
+                     vcopy, axpy, scal, dot, dotu, norm2, asum, vswap, iamax, rot, rotg, rotm, rotmg, gemv, geam, dgmm, tbsv, sparse_gemv,
                      solve_cg, solve_gmres)

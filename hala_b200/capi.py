@@ -62,6 +62,10 @@ SIGNATURES = {
     "hb_sptrsv": (_i, [_vp, _vp, C.c_char, _vp, _vp, _i, _vp, _i]),
     "hb_sptrsm": (_i, [_vp, _vp, C.c_char, C.c_char, _i, _vp, _vp, _i]),
     "hb_ilu0": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hb_spmm": (_i, [_vp, _vp, C.c_char, C.c_char, _i, _i, _vp, _vp, _i, _vp, _vp, _i]),
+    "hb_geam": (_i, [_vp, _i, C.c_char, C.c_char, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i]),
+    "hb_dgmm": (_i, [_vp, _i, C.c_char, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
+    "hb_tbsv": (_i, [_vp, _i, C.c_char, C.c_char, C.c_char, _i, _i, _vp, _i, _vp, _i]),
     "hb_copy": (_i, [_vp, _i, _i, _vp, _i, _vp, _i]),
     "hb_axpy": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i]),
     "hb_scal": (_i, [_vp, _i, _i, _vp, _vp, _i]),

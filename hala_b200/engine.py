@@ -264,6 +264,24 @@ def gemv(engine, trans, M, N, alpha, A, x, beta, y, lda=-1, incx=1, incy=1):
                       _host_ptr(b), _dptr(y), incy), "hb_gemv")
 
 
+def geam(engine, transa, transb, M, N, alpha, A, lda, beta, B, ldb, Cm, ldc):
+    if Cm.size() < ldc * N:
+        Cm.resize(ldc * N)
+    a, b = _sc(alpha, A.dtype), _sc(beta, A.dtype)
+    check(lib.hb_geam(engine.ctx, _CODE[A.dtype], transa.encode(), transb.encode(), M, N, _host_ptr(a), A.ptr, lda, _host_ptr(b), B.ptr, ldb,
+                      Cm.ptr, ldc), "hb_geam")
+
+
+def dgmm(engine, side, M, N, A, lda, x, incx, Cm, ldc):
+    if Cm.size() < ldc * N:
+        Cm.resize(ldc * N)
+    check(lib.hb_dgmm(engine.ctx, _CODE[A.dtype], side.encode(), M, N, A.ptr, lda, x.ptr, incx, Cm.ptr, ldc), "hb_dgmm")
+
+
+def tbsv(engine, uplo, trans, diag, N, k, A, lda, x, incx=1):
+    check(lib.hb_tbsv(engine.ctx, _CODE[A.dtype], uplo.encode(), trans.encode(), diag.encode(), N, k, A.ptr, lda, x.ptr, incx), "hb_tbsv")
+
+
 # ---------------------------------------------------------------- sparse (gpu/hala_cuda_sparse_general.hpp)
 class gpu_sparse_matrix:
     """Non-owning CSR view + one-time analysis (the vectors must outlive the matrix, as in the reference)."""
@@ -295,6 +313,15 @@ class gpu_sparse_matrix:
         b = C.c_size_t(0)
         check(lib.hb_spmv_buffer_size(self.h, trans.encode(), C.byref(b)), "hb_spmv_buffer_size")
         return b.value
+
+    def gemm(self, transa, transb, b_rows, b_cols, alpha, B, ldb, beta, Cm, ldc, work=None):
+        """C = alpha op(A) op(B) + beta C (reference gpu_sparse_matrix::gemm, :302-332)"""
+        N = b_cols if transb in "Nn" else b_rows
+        if beta == 0 and Cm.size() < ldc * N:
+            Cm.resize(ldc * N)
+        a, b = _sc(alpha, self.dtype), _sc(beta, self.dtype)
+        check(lib.hb_spmm(self.engine.ctx, self.h, transa.encode(), transb.encode(), b_rows, b_cols, _host_ptr(a), B.ptr, ldb,
+                          _host_ptr(b), Cm.ptr, ldc), "hb_spmm")
 
     def gemv(self, trans, alpha, x, beta, y, work=None):
         ny = self.rows if trans in "Nn" else self.cols

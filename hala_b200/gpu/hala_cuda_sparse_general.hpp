@@ -71,15 +71,30 @@ public:
         hb_scalar<value_type, FPb> b(beta);
         check_hb(hb_spmv(rengine, handle, trans_to_hb<value_type>(trans), a.get(), get_data(x), b.get(), get_data(y)), "hala::gpu_sparse_matrix::gemv()");
     }
-    // sparse matrix - dense matrix product (cusparseSpMM in the reference, :302-332) belongs to batch CG: SURVEY.md §8 row f2
+    // sparse matrix - dense matrix product (reference :284-332, cusparseSpMM) -> hb_spmm; no work buffer
     template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC>
-    size_t gemm_buffer_size(char, char, int, int, FSA, VectorLikeB const&, int, FSB, VectorLikeC&, int) const{
-        HALAB200_OUT_OF_SCOPE(FSA, "hala::gpu_sparse_matrix::gemm()");
+    size_t gemm_buffer_size(char transa, char transb, int b_rows, int b_cols, FSA, VectorLikeB const &B, int, FSB beta, VectorLikeC &C, int ldc) const{
+        check_types(B, C);
+        rengine.check_gpu(B, C);
+        int N = (is_n(transb)) ? b_cols : b_rows;
+        (void) transa;
+        pntr_check_set_size(beta, C, ldc, N);
         return 0;
     }
-    template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC, class... Rest>
-    void gemm(char, char, int, int, FSA, VectorLikeB const&, int, FSB, VectorLikeC&, int, Rest&&...) const{
-        HALAB200_OUT_OF_SCOPE(FSA, "hala::gpu_sparse_matrix::gemm()");
+    template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC, class VectorLikeT>
+    void gemm(char transa, char transb, int b_rows, int b_cols, FSA alpha, VectorLikeB const &B, int ldb, FSB beta, VectorLikeC &C, int ldc, VectorLikeT &&) const{
+        gemm(transa, transb, b_rows, b_cols, alpha, B, ldb, beta, C, ldc);
+    }
+    template<typename FSA, class VectorLikeB, typename FSB, class VectorLikeC>
+    void gemm(char transa, char transb, int b_rows, int b_cols, FSA alpha, VectorLikeB const &B, int ldb, FSB beta, VectorLikeC &C, int ldc) const{
+        check_types(B, C);
+        rengine.check_gpu(B, C);
+        int N = (is_n(transb)) ? b_cols : b_rows;
+        pntr_check_set_size(beta, C, ldc, N);
+        hb_scalar<value_type, FSA> a(alpha);
+        hb_scalar<value_type, FSB> b(beta);
+        check_hb(hb_spmm(rengine, handle, trans_to_hb<value_type>(transa), trans_to_hb<value_type>(transb), b_rows, b_cols, a.get(), get_data(B), ldb,
+                         b.get(), get_data(C), ldc), "hala::gpu_sparse_matrix::gemm()");
     }
 
 private:
@@ -120,10 +135,19 @@ void sparse_gemv(gpu_engine const &engine, char trans, int M, int N,
     make_sparse_matrix(engine, M, N, get_size_int(indx), pntr, indx, vals).gemv(trans, alpha, x, beta, y);
 }
 
+//! One-shot SpMM (reference :444-457): a temporary view per call.
 template<typename FSA, class VectorLikeP, class VectorLikeI, class VectorLikeV, class VectorLikeB, typename FSB, class VectorLikeC>
-void sparse_gemm(gpu_engine const&, char, char, int, int, int, FSA, VectorLikeP const&, VectorLikeI const&, VectorLikeV const&,
-                 VectorLikeB const&, int, FSB, VectorLikeC&, int){
-    HALAB200_OUT_OF_SCOPE(FSA, "hala::sparse_gemm(gpu_engine)");
+void sparse_gemm(gpu_engine const &engine, char transa, char transb, int M, int N, int K,
+                 FSA alpha, VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals,
+                 VectorLikeB const &B, int ldb, FSB beta, VectorLikeC &C, int ldc){
+    check_types(vals, B, C);
+    check_types_int(pntr, indx);
+    engine.check_gpu(pntr, indx, vals, B, C);
+    pntr_check_set_size(beta, C, ldc, N);
+    int nnz = get_size_int(indx);
+    assert( valid::sparse_gemm(transa, transb, M, N, K, nnz, pntr, indx, vals, B, ldb, C, ldc) );
+    make_sparse_matrix(engine, (is_n(transa)) ? M : K, (is_n(transa)) ? K : M, nnz, pntr, indx, vals)
+        .gemm(transa, transb, (is_n(transb)) ? K : N, (is_n(transb)) ? N : K, alpha, B, ldb, beta, C, ldc);
 }
 
 }

@@ -22,9 +22,14 @@ void gemv(gpu_engine const &engine, char trans, int M, int N, FPA alpha, VectorL
              "hala::gemv(gpu_engine)");
 }
 
+// tbsv (reference :368-388, cublas?tbsv): bandwidth 0 is the element-wise divide of hala::vdivide (wax/hala_blas_extensions.hpp:251-260)
 template<class VectorLikeA, class VectorLikeX>
-inline void tbsv(gpu_engine const&, char, char, char, int, int, VectorLikeA const&, int, VectorLikeX&&, int){
-    HALAB200_OUT_OF_SCOPE(VectorLikeA, "hala::tbsv(gpu_engine)");
+inline void tbsv(gpu_engine const &engine, char uplo, char trans, char diag, int N, int k, VectorLikeA const &A, int lda, VectorLikeX &&x, int incx){
+    check_types(A, x);
+    engine.check_gpu(A, x);
+    assert( valid::tbmsv(uplo, trans, diag, N, k, A, lda, x, incx) );
+    using scalar_type = get_scalar_type<VectorLikeA>;
+    check_hb(hb_tbsv(engine, hb_type<scalar_type>(), uplo, trans, diag, N, k, get_data(A), lda, get_data(x), incx), "hala::tbsv(gpu_engine)");
 }
 
 }

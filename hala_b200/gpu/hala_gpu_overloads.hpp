@@ -60,15 +60,20 @@ void gemv(gpu_engine const &engine, char trans, int M, int N,
     gemv(engine, trans, M, N, alpha, A, lda, x, incx, beta, y, incy);
 }
 
-// names the wax templates mention with default arguments (batch helpers, SURVEY §8b gotcha 2): declared, out of scope on use
+// default-argument forms of the batch helpers (reference gpu/hala_gpu_overloads.hpp:31-46)
 template<typename FPa, class VectorLikeA, typename FPb, class VectorLikeB, class VectorLikeC>
 inline void geam(gpu_engine const &engine, char transa, char transb, int M, int N, FPa alpha, VectorLikeA const &A,
                  FPb beta, VectorLikeB const &B, VectorLikeC &&C, int lda = -1, int ldb = -1, int ldc = -1){
+    valid::default_ld(is_n(transa), M, N, lda);
+    valid::default_ld(is_n(transb), M, N, ldb);
+    valid::default_ld(M, ldc);
     geam(engine, transa, transb, M, N, alpha, A, lda, beta, B, ldb, C, ldc);
 }
 template<class VectorLikeA, class VectorLikeB, class VectorLikeC>
 inline void dgmm(gpu_engine const &engine, char side, int M, int N, VectorLikeA const &A,
                  VectorLikeB const &x, VectorLikeC &&C, int lda = -1, int incx = 1, int ldc = -1){
+    valid::default_ld(M, lda);
+    valid::default_ld(M, ldc);
     dgmm(engine, side, M, N, A, lda, x, incx, C, ldc);
 }
 template<class VectorLikeX, class VectorLikeY>
@@ -89,6 +94,15 @@ void rotm(gpu_engine const &engine, VectorLikeX &x, VectorLikeY &&y, VectorLikeP
 template<class VectorLikeX> inline int iamax(gpu_engine const &engine, VectorLikeX const &x, int incx = 1, int N = -1){
     valid::default_size(x, incx, N);
     return iamax(engine, N, x, incx);
+}
+// default-argument form of the one-shot SpMM (reference gpu/hala_gpu_overloads.hpp:390-397)
+template<typename FSA, class VectorLikeP, class VectorLikeI, class VectorLikeV, class VectorLikeB, typename FSB, class VectorLikeC>
+inline void sparse_gemm(gpu_engine const &engine, char transa, char transb, int M, int N, int K,
+                        FSA alpha, VectorLikeP const &pntr, VectorLikeI const &indx, VectorLikeV const &vals,
+                        VectorLikeB const &B, FSB beta, VectorLikeC &&C, int ldb = -1, int ldc = -1){
+    valid::default_ld(is_n(transb), K, N, ldb);
+    valid::default_ld(M, ldc);
+    sparse_gemm(engine, transa, transb, M, N, K, alpha, pntr, indx, vals, B, ldb, beta, C, ldc);
 }
 template<class VectorLikeA, class VectorLikeX>
 inline void tbsv(gpu_engine const &engine, char uplo, char trans, char diag, int N, int k, const VectorLikeA &A, VectorLikeX &&x, int lda = -1, int incx = 1){

@@ -109,6 +109,20 @@ int hb_sptrsv(hb_ctx *ctx, hb_tri *tri, char trans, const void *alpha, const voi
 int hb_sptrsm(hb_ctx *ctx, hb_tri *tri, char transa, char transb, int nrhs, const void *alpha, void *B, int ldb);
 int hb_ilu0(hb_ctx *ctx, int dtype, int rows, int nnz, const int *pntr, const int *indx, const void *vals, void *ilu);
 
+/* ---- multi right-hand-side pieces of the batch solvers ----
+ * hb_spmm : C = alpha op(A) op(B) + beta C; C is M x N column-major (ldc), op(A) is M x K, B is stored b_rows x b_cols (ldb) and
+ *   op(B) is K x N — gpu_sparse_matrix::gemm -> cusparseSpMM (gpu/hala_cuda_sparse_general.hpp:284-332).  C is not read when beta == 0.
+ * hb_geam : C = alpha op(A) + beta op(B), M x N    — cublas?geam (gpu/hala_gpu_blas0.hpp:46-72)
+ * hb_dgmm : C = diag(x) A ('L') or A diag(x) ('R') — cublas?dgmm (gpu/hala_gpu_blas0.hpp:79-103)
+ * hb_tbsv : x <- op(A)^-1 x, A triangular banded with k off-diagonals in BLAS band storage — cublas?tbsv (gpu/hala_gpu_blas2.hpp);
+ *   k == 0 is the element-wise divide behind hala::vdivide (wax/hala_blas_extensions.hpp:251-260) */
+int hb_spmm(hb_ctx *ctx, const hb_csr *csr, char transa, char transb, int b_rows, int b_cols, const void *alpha,
+            const void *B, int ldb, const void *beta, void *C, int ldc);
+int hb_geam(hb_ctx *ctx, int dtype, char transa, char transb, int M, int N, const void *alpha, const void *A, int lda,
+            const void *beta, const void *B, int ldb, void *C, int ldc);
+int hb_dgmm(hb_ctx *ctx, int dtype, char side, int M, int N, const void *A, int lda, const void *x, int incx, void *C, int ldc);
+int hb_tbsv(hb_ctx *ctx, int dtype, char uplo, char trans, char diag, int n, int k, const void *A, int lda, void *x, int incx);
+
 /* ---- BLAS-1: gpu/hala_gpu_blas1.hpp  vcopy :48-65, norm2 :102-121, dot<conj> :178-198, axpy :204-222, scal :228-245 ---- */
 int hb_copy(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *y, int incy);
 int hb_axpy(hb_ctx *ctx, int dtype, int n, const void *alpha, const void *x, int incx, void *y, int incy);

@@ -19,6 +19,10 @@ def build(with_ref=True):
                    stdout=subprocess.DEVNULL)
 
 
+def C_char(c):
+    return C.c_char(c.encode())
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -89,6 +93,29 @@ class _Lib:
                               _ptr(yy) if yy is not None else None, int(incy), _ptr(res))
         assert rc == 0, rc
         return res[0] if op in ("dot", "dotu", "nrm2") else yy
+
+    def spmm(self, transa, transb, M, N, K, pntr, indx, vals, B, ldb, alpha=1.0, beta=0.0, C=None, ldc=None):
+        """C (M x N, column-major, ldc) = alpha op(A) op(B) + beta C  (sparse/hala_sparse_utils.hpp:120-160); B, C flat column-major"""
+        dt = vals.dtype
+        ldc = M if ldc is None else ldc
+        out = np.zeros(ldc * N, dtype=dt) if C is None else np.array(C, dtype=dt, copy=True)
+        a, b = _scalar(alpha, dt), _scalar(beta, dt)
+        ch = lambda c: C_char(c)
+        rc = self._f("spmm")(CODE[dt], C_char(transa), C_char(transb), M, N, K, _ptr(a), int(indx.size), _ptr(pntr), _ptr(indx), _ptr(vals),
+                             _ptr(np.ascontiguousarray(B, dtype=dt)), int(ldb), _ptr(b), _ptr(out), int(ldc))
+        assert rc == 0, rc
+        return out
+
+    def batch_cg(self, pntr, indx, vals, B, nrhs, tol, max_iter=10**6):
+        """reference only: hala::solve_batch_cg with the identity preconditioner; B flat column-major rows x nrhs. Returns (X, iterations)."""
+        dt = vals.dtype
+        n = pntr.size - 1
+        X = np.zeros(n * nrhs, dtype=dt)
+        it = C.c_int(0)
+        rc = self._f("batch_cg")(CODE[dt], n, int(indx.size), int(nrhs), _ptr(pntr), _ptr(indx), _ptr(vals), _ptr(np.ascontiguousarray(B, dtype=dt)),
+                                 _ptr(X), C.c_double(tol), int(max_iter), C.byref(it))
+        assert rc == 0, rc
+        return X, it.value
 
     def trsv(self, uplo, diag, trans, pntr, indx, vals, b, alpha=1.0, general=False):
         """x = alpha * op(T)^-1 b.  general=False: CSR holds one triangle, diagonal last (L) / first (U) — the reference's layout

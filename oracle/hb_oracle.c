@@ -188,4 +188,15 @@ int orc_ilu_apply(int dtype, int n, const int *pntr, const int *indx, const int 
     return 0;
 }
 
+int orc_spmm(int dtype, char transa, char transb, int M, int N, int K, const void *alpha, int nnz, const int *pntr, const int *indx,
+             const void *vals, const void *B, int ldb, const void *beta, void *C, int ldc){
+    (void) nnz;
+    SW(dtype,
+       spmm_s(transa, transb, M, N, K, *(const float*) alpha, pntr, indx, vals, B, ldb, *(const float*) beta, C, ldc),
+       spmm_d(transa, transb, M, N, K, *(const double*) alpha, pntr, indx, vals, B, ldb, *(const double*) beta, C, ldc),
+       spmm_c(transa, transb, M, N, K, *(const float _Complex*) alpha, pntr, indx, vals, B, ldb, *(const float _Complex*) beta, C, ldc),
+       spmm_z(transa, transb, M, N, K, *(const double _Complex*) alpha, pntr, indx, vals, B, ldb, *(const double _Complex*) beta, C, ldc))
+    return 0;
+}
+
 const char* orc_version(void){ return "hala_b200 CPU oracle (restatement of LIBHALA/hala 1.1.0 cpu_engine path)"; }

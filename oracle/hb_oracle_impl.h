@@ -344,3 +344,21 @@ static void NAME(ilu_apply)(int n, const int *pntr, const int *indx, const int *
         x[i] /= ilu[diag[i]];
     }
 }
+
+/* sparse/hala_sparse_utils.hpp:120-160 sparse_gemm_array: C = alpha op(A) op(B) + beta C, one sparse_gemv_array per column of C;
+ * op(B) = B^T / B^H first copies the row of B into a contiguous (conjugated) vector. C is M x N (ldc), op(A) is M x K. */
+static void NAME(spmm)(char transa, char transb, int M, int N, int K, T alpha, const int *pntr, const int *indx, const T *vals,
+                       const T *B, int ldb, T beta, T *C, int ldc){
+    const int an = (transa == 'N' || transa == 'n'), bn = (transb == 'N' || transb == 'n'), bc = (transb == 'C' || transb == 'c');
+    T *x = (T*) malloc(sizeof(T) * (size_t) (K > 0 ? K : 1));
+    for(int i=0; i<N; i++){
+        const T *col = B + (size_t) i * ldb;
+        if (!bn){
+            for(int k=0; k<K; k++){ T v = B[i + (size_t) k * ldb]; x[k] = bc ? CONJ(v) : v; }
+            col = x;
+        }
+        if (an) NAME(spmv)('N', M, K, alpha, pntr, indx, vals, col, beta, C + (size_t) i * ldc);
+        else    NAME(spmv)(transa, K, M, alpha, pntr, indx, vals, col, beta, C + (size_t) i * ldc);
+    }
+    free(x);
+}

@@ -12,6 +12,8 @@
 //   ref_cg     -> hala::solve_cg(cpu_engine, ...)         hex/solvers/hala_solvers_cg.hpp:232-246 -> :181-227 -> solve_cg_core :92-156
 //   ref_gmres  -> hala::solve_gmres(cpu_engine, ...)      hex/solvers/hala_solvers_gmres.hpp:127-230
 //   ref_trsv   -> hala::sparse_trsv(cpu_triangular_matrix) sparse/hala_sparse_structs.hpp:257-269 -> sparse_trsv_array (hala_sparse_utils.hpp:283-335)
+//   ref_spmm   -> hala::sparse_gemm(cpu_engine)           sparse/hala_sparse_utils.hpp:120-160
+//   ref_batch_cg -> hala::solve_batch_cg(cpu_engine)      hex/solvers/hala_solvers_cg_batch.hpp:68-151
 //   ref_ilu    -> factorize_ilu + make_ilu(cpu_engine).apply sparse/hala_sparse_ilu.hpp -> hala_sparse_utils.hpp:228-274
 // The preconditioner is the identity lambda SURVEY.md §8(d) prescribes: hala::vcopy(engine, in, out).
 //
@@ -149,6 +151,32 @@ int ilu(int n, int nnz, const int *pntr, const int *indx, const void *vals, void
     return 0;
 }
 
+// hala::sparse_gemm(cpu_engine) -> sparse_gemm_array (sparse/hala_sparse_utils.hpp:120-160)
+template<typename T>
+int spmm(char transa, char transb, int M, int N, int K, const void *alpha, int nnz, const int *pntr, const int *indx, const void *vals,
+         const void *B, int ldb, const void *beta, void *C, int ldc){
+    hala::cpu_engine e;
+    bool an = (transa == 'N' || transa == 'n'), bn = (transb == 'N' || transb == 'n');
+    view<const int> vp(pntr, (size_t) (an ? M : K) + 1), vi(indx, (size_t) nnz);
+    view<const T> vv((T const*) vals, (size_t) nnz), vB((T const*) B, (size_t) ldb * (size_t) (bn ? N : K));
+    view<T> vC((T*) C, (size_t) ldc * (size_t) N);
+    hala::sparse_gemm(e, transa, transb, M, N, K, rd<T>(alpha), vp, vi, vv, vB, ldb, rd<T>(beta), vC, ldc);
+    return 0;
+}
+// hala::solve_batch_cg(cpu_engine) with the identity preconditioner (hex/solvers/hala_solvers_cg_batch.hpp:68-151)
+template<typename T>
+int batch_cg(int nrows, int nnz, int nrhs, const int *pntr, const int *indx, const void *vals, const void *B, void *X, double tol, int max_iter, int *iters){
+    hala::cpu_engine e;
+    using P = typename hala::define_standard_precision<T>::value_type;
+    view<const int> vp(pntr, (size_t) nrows + 1), vi(indx, (size_t) nnz);
+    view<const T> vv((T const*) vals, (size_t) nnz), vB((T const*) B, (size_t) nrows * (size_t) nrhs);
+    view<T> vX((T*) X, (size_t) nrows * (size_t) nrhs);
+    hala::stop_criteria<P> stop((P) tol, max_iter);
+    *iters = hala::solve_batch_cg(e, stop, vp, vi, vv,
+                                  [&](auto const &in, auto &out)->void{ hala::vcopy(e, in, out); }, vB, vX);
+    return 0;
+}
+
 #define DISPATCH(dtype, call) \
     switch(dtype){ \
         case 0: { using T = float; return call; } \
@@ -187,6 +215,14 @@ int RNAME(trsv)(int dtype, char uplo, char diag, char trans, int n, const void *
 }
 int RNAME(ilu)(int dtype, int n, int nnz, const int *pntr, const int *indx, const void *vals, void *ilu_out, const void *x, void *r){
     try{ DISPATCH(dtype, ilu<T>(n, nnz, pntr, indx, vals, ilu_out, x, r)) }catch(...){ return 3; }
+}
+int RNAME(spmm)(int dtype, char transa, char transb, int M, int N, int K, const void *alpha, int nnz, const int *pntr, const int *indx,
+                const void *vals, const void *B, int ldb, const void *beta, void *C, int ldc){
+    try{ DISPATCH(dtype, spmm<T>(transa, transb, M, N, K, alpha, nnz, pntr, indx, vals, B, ldb, beta, C, ldc)) }catch(...){ return 3; }
+}
+int RNAME(batch_cg)(int dtype, int nrows, int nnz, int nrhs, const int *pntr, const int *indx, const void *vals, const void *B, void *X,
+                    double tol, int max_iter, int *iters){
+    try{ DISPATCH(dtype, batch_cg<T>(nrows, nnz, nrhs, pntr, indx, vals, B, X, tol, max_iter, iters)) }catch(...){ return 3; }
 }
 const char* RNAME(version)(){ return "LIBHALA/hala " HALA_VERSION_STRING " cpu_engine"; }
 

@@ -27,6 +27,12 @@ def golden_f1():
 
 
 @pytest.fixture(scope="session")
+def golden_f2():
+    """SpMM / batch-CG outputs of the unmodified reference (tests/golden/make_golden.py f2)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs_f2.npz"))
+
+
+@pytest.fixture(scope="session")
 def ref_tests():
     """Vectors harvested from the reference's own tests (file:line inside the JSON)."""
     with open(os.path.join(ROOT, "tests", "golden", "ref_tests.json")) as f:

@@ -10,10 +10,13 @@
 //   tests/blas1_tests.hpp       test_vcopy, test_vswap, test_axpy, test_rscalar, test_scal, test_iamax, test_rotate
 //                               with mixed_engine, engine + no-engine API, strides
 //   tests/sparse_tests.hpp      test_sparse_gemv, test_sparse_trsv, test_sparse_trsm   with mixed_engine, N/T/C
-//   tests/solvers_tests.hpp     test_cg, test_gmres              the reference's ILU-preconditioned solver tests, mixed_engine
+//   tests/solvers_tests.hpp     test_cg, test_cg_batch, test_gmres   the reference's ILU-preconditioned solver tests, mixed_engine
+//   tests/cuda_blas0_tests.hpp  transpose, test_geam, test_dgmm  (dense helpers of the batch solvers)
+//   tests/sparse_tests.hpp      test_sparse_gemm, test_batch_axpy / dot / max_norm / scale   (SpMM and the wax batch templates on top of our primitives)
 // plus solver checks written here: solve_cg / solve_gmres (reference templates, identity preconditioner) on gpu_engine and
 // mixed_engine against cpu_engine, 4 scalar types.
 #include "cuda_core_tests.hpp"
+#include "cuda_blas0_tests.hpp"
 #include "cuda_blas1_tests.hpp"
 #include "cuda_blas2_tests.hpp"
 #include "cuda_sparse_tests.hpp"
@@ -118,6 +121,15 @@ int main(int argc, char**){
         [&]()->void{ eng_api::test_sparse_trsv<float, 0>(emixed); eng_api::test_sparse_trsv<double, 0>(emixed); eng_api::test_sparse_trsv<std::complex<float>, 0>(emixed); eng_api::test_sparse_trsv<std::complex<double>, 0>(emixed); },
         [&]()->void{ eng_api::test_sparse_trsm<float, 0>(emixed); eng_api::test_sparse_trsm<double, 0>(emixed); eng_api::test_sparse_trsm<std::complex<float>, 0>(emixed); eng_api::test_sparse_trsm<std::complex<double>, 0>(emixed); },
         [&]()->void{ test_cg<float>(emixed); test_cg<double>(emixed); test_cg<std::complex<float>>(emixed); test_cg<std::complex<double>>(emixed); },
+        [&]()->void{ transpose<float>(); transpose<double>(); transpose<std::complex<float>>(); transpose<std::complex<double>>(); },
+        [&]()->void{ test_geam<float>(); test_geam<double>(); test_geam<std::complex<float>>(); test_geam<std::complex<double>>(); },
+        [&]()->void{ test_dgmm<float>(); test_dgmm<double>(); test_dgmm<std::complex<float>>(); test_dgmm<std::complex<double>>(); },
+        [&]()->void{ eng_api::test_sparse_gemm<float, 0>(emixed); eng_api::test_sparse_gemm<double, 0>(emixed); eng_api::test_sparse_gemm<std::complex<float>, 0>(emixed); eng_api::test_sparse_gemm<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_batch_axpy<float, 0>(emixed); eng_api::test_batch_axpy<double, 0>(emixed); eng_api::test_batch_axpy<std::complex<float>, 0>(emixed); eng_api::test_batch_axpy<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_batch_dot<float, 0>(emixed); eng_api::test_batch_dot<double, 0>(emixed); eng_api::test_batch_dot<std::complex<float>, 0>(emixed); eng_api::test_batch_dot<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_batch_max_norm<float, 0>(emixed); eng_api::test_batch_max_norm<double, 0>(emixed); eng_api::test_batch_max_norm<std::complex<float>, 0>(emixed); eng_api::test_batch_max_norm<std::complex<double>, 0>(emixed); },
+        [&]()->void{ eng_api::test_batch_scale<float, 0>(emixed); eng_api::test_batch_scale<double, 0>(emixed); eng_api::test_batch_scale<std::complex<float>, 0>(emixed); eng_api::test_batch_scale<std::complex<double>, 0>(emixed); },
+        [&]()->void{ test_cg_batch<float>(emixed); test_cg_batch<double>(emixed); test_cg_batch<std::complex<float>>(emixed); test_cg_batch<std::complex<double>>(emixed); },
         [&]()->void{ test_gmres<float>(emixed); test_gmres<double>(emixed); test_gmres<std::complex<float>>(emixed); test_gmres<std::complex<double>>(emixed); },
     };
     for(auto const &t : f1) perform(t);

@@ -231,3 +231,18 @@ def test_oracle_trsv_ilu_reference_test_vectors(orc, dt):
     fac, r = orc.ilu(p, i, np.array([3, 2, 1, 2, 4, 3, 2, 1, 6], dtype=t), np.array([1, 2, 3], dtype=t))
     np.testing.assert_allclose(fac, [3, 2, 1, 2 / 3, 8 / 3, 7 / 3, 2 / 3, -0.125, 5.625], rtol=1e-5 if "32" in dt else 1e-13)
     np.testing.assert_allclose(r, [1 / 9, 1 / 9, 4 / 9], rtol=1e-5 if "32" in dt else 1e-13)
+
+
+# ---------------------------------------------------------------- SpMM
+@pytest.mark.parametrize("dt", DT)
+def test_oracle_spmm_matches_recorded_reference(orc, golden_f2, dt):
+    p, i, v = mg.perturbed("convdiff7", 7, dt)
+    n, N = p.size - 1, 5
+    for ta in "NTC":
+        for tb in "NTC":
+            ldb = n + 3 if tb == "N" else N + 2
+            B = mg.probe_x(ldb * (N if tb == "N" else n), dt, seed=5)
+            C0 = mg.probe_x((n + 1) * N, dt, seed=6)
+            got = orc.spmm(ta, tb, n, N, n, p, i, v, B, ldb, alpha=1.5, beta=0.5, C=C0, ldc=n + 1)
+            want = golden_f2[f"spmm/convdiff7:7/{dt}/{ta}{tb}"]
+            assert np.abs(got - want).max() <= F1_TOL[dt] * np.abs(want).max(), (ta, tb)
