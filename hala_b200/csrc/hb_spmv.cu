@@ -318,7 +318,7 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                                             A->pipe_contiguous ? A->cta_rows[CFG] : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip,
                                                             (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols,
-                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch);
+                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -331,6 +331,54 @@ static int launch_pipe(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_ar
         case 2:  return launch_pipe_cfg<T, CFG, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         default: return launch_pipe_cfg<T, CFG, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
     }
+}
+
+// ---- interleaved multi right-hand-side product (hb_spmm fast path): Ct[row][kb] = sum_j a_ij Bt[col_j][kb], kb < NBP
+template<typename T, int CFG, int TPR, int NBP>
+static int launch_pipe_mm_cfg(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t ldbt, T *Ct, size_t ldct){
+    using C = pipe_cfg<CFG>;
+    const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, false, NBP>;
+    static bool configured = false;
+    if (!configured){
+        HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
+    scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
+    k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, Bt, Ct, one, zero,
+                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct);
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+template<typename T, int CFG, int NBP>
+static int launch_pipe_mm(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t ldbt, T *Ct, size_t ldct){
+    switch (pipe_tpr(A->mean_row_nnz, sizeof(T))){
+        case 16: return launch_pipe_mm_cfg<T, CFG, 16, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
+        case 8:  return launch_pipe_mm_cfg<T, CFG, 8, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
+        case 4:  return launch_pipe_mm_cfg<T, CFG, 4, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
+        case 2:  return launch_pipe_mm_cfg<T, CFG, 2, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
+        default: return launch_pipe_mm_cfg<T, CFG, 1, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
+    }
+}
+int hb_spmv_variant(const hb_csr *A);
+// can the interleaved streaming kernel take this matrix?  (pipeline available, every tile fits its stage, no warp / CTA rows)
+bool hb_spmm_interleaved_ok(const hb_csr *A){
+    if (hb_spmv_variant(A) != 3) return false;
+    const size_t es = hb_dtype_size(A->dtype);
+    const int threads = A->pipe_cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
+    const int rows_per_tile = threads / pipe_tpr(A->mean_row_nnz, es);
+    const long long cap = (long long) threads * (es == 16 ? 4 : 8);
+    return A->max_row_nnz < PIPE_WARPROW && (long long) rows_per_tile * A->max_row_nnz + 4 <= cap;
+}
+// nbp = 4 or 8 interleaved right-hand sides (a multiple of the 128-bit packet); Bt: cols x nbp (ldbt), Ct: rows x nbp (ldct)
+int hb_spmm_interleaved(hb_ctx *ctx, const hb_csr *A, int nbp, const void *Bt, size_t ldbt, void *Ct, size_t ldct){
+    HB_DISPATCH(A->dtype, {
+        if (A->pipe_cfg == 0) return nbp == 8 ? launch_pipe_mm<T, 0, 8>(ctx, A, (const T*) Bt, ldbt, (T*) Ct, ldct) : launch_pipe_mm<T, 0, 4>(ctx, A, (const T*) Bt, ldbt, (T*) Ct, ldct);
+        return nbp == 8 ? launch_pipe_mm<T, 1, 8>(ctx, A, (const T*) Bt, ldbt, (T*) Ct, ldct) : launch_pipe_mm<T, 1, 4>(ctx, A, (const T*) Bt, ldbt, (T*) Ct, ldct);
+    });
+    return HB_OK;
 }
 
 // resident CTAs per SM of the instantiation that will run (asked of the driver, not guessed): the persistent grid and its

@@ -41,12 +41,16 @@ __global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int til
     cta_tiles[g] = lo;
 }
 
-template<typename T, int THREADS, int TPR, int STAGES, bool DOT>
+// NBP > 0 turns the same kernel into the multi right-hand-side product of the batch solvers (hb_spmm): x is then the row-major
+// ("interleaved") block Bt[col * ldx + kb], kb < NBP, so the NBP operands of one non-zero are ONE contiguous 128-bit-packet gather,
+// and y the interleaved result Ct[row * ldy + kb]; the matrix stream is shared by all NBP right-hand sides.  The host only
+// launches it when every tile fits its stage and no row is long enough for the warp / CTA paths.
+template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
                                                             void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
-                                                            const peer_view *pv, unsigned long long epoch){
+                                                            const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy){
     constexpr int ROWS = THREADS / TPR;
     constexpr int CAP  = THREADS * pipe_slots<T>();
     constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
@@ -153,6 +157,53 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             int rs = 0, re = 0;
             if (myrow < rows){ rs = sp[grp]; re = sp[grp + 1]; }
             T sum = zero_of<T>();
+            if constexpr (NBP > 0){
+                constexpr int NV = vec16<T>::N, NPK = NBP / NV, MU = (NPK >= 4 ? 2 : 4);    // packets per entry; entries per lane in flight
+                static_assert(NBP % NV == 0, "interleaved block must be whole 128-bit packets");
+                T sums[NBP];
+                #pragma unroll
+                for (int e = 0; e < NBP; e++) sums[e] = zero_of<T>();
+                const T *sv = stage_vals(s); const int *sc = stage_cols(s);
+                const int end = re - a0;
+                for (int base = rs + sub - a0; base < end; base += MU * TPR){
+                    T v[MU]; vec16<T> pk[MU][NPK]; bool ok[MU];
+                    #pragma unroll
+                    for (int u = 0; u < MU; u++){
+                        ok[u] = (base + u * TPR) < end;
+                        if (ok[u]){
+                            v[u] = sv[base + u * TPR];
+                            const vec16<T> *bp = reinterpret_cast<const vec16<T>*>(x + (size_t) sc[base + u * TPR] * ldx);
+                            #pragma unroll
+                            for (int q = 0; q < NPK; q++) pk[u][q] = bp[q];
+                        }
+                    }
+                    #pragma unroll
+                    for (int u = 0; u < MU; u++) if (ok[u]){
+                        #pragma unroll
+                        for (int q = 0; q < NPK; q++){
+                            #pragma unroll
+                            for (int e = 0; e < NV; e++) sums[q * NV + e] = hfma(v[u], pk[u][q].v[e], sums[q * NV + e]);
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int e = 0; e < NBP; e++){
+                    #pragma unroll
+                    for (int d = TPR / 2; d > 0; d >>= 1) sums[e] = hadd(sums[e], shfl_down(sums[e], d));
+                }
+                if (sub == 0 && myrow < rows){
+                    vec16<T> *cp = reinterpret_cast<vec16<T>*>(y + (size_t) myrow * ldy);
+                    #pragma unroll
+                    for (int q = 0; q < NPK; q++){
+                        vec16<T> o;
+                        #pragma unroll
+                        for (int e = 0; e < NV; e++) o.v[e] = sums[q * NV + e];
+                        cp[q] = o;
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
             if (a0 >= 0){
                 const T *sv = stage_vals(s); const int *sc = stage_cols(s);
                 // batches of PIPE_UNR entries per lane: all shared-memory reads, then all gathers, then the FMAs (two
