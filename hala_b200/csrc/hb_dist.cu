@@ -69,6 +69,7 @@ struct hb_dist {
     void  *peer_base[HB_MAX_PEERS] = {};// rank q's exchange buffer as mapped into this process (q == rank: pbuf)
     peer_view *pv_dev = nullptr;
     unsigned long long epoch = 0;       // global iteration number of the peer protocol; same on every rank
+    unsigned long long vepoch = 0;      // number of peer vector all-reduces so far; same on every rank
     int    plan_version = 0;
 };
 
@@ -294,6 +295,9 @@ static int dgrid(const hb_ctx *ctx, long long n, int per_block){
     return (int) (need < cap ? need : cap);
 }
 
+extern "C" int hb_dist_halo_exchange_nccl(hb_dist *d, int dtype, void *x_ext);
+extern "C" int hb_dist_allreduce_sum_nccl(hb_dist *d, int dtype, void *dev_scalars, int count);
+
 // ------------------------------------------------------------------------------------------------ peer transport: setup
 namespace {
 struct peer_info {                              // what every rank tells every other one (all-gathered through NCCL)
@@ -449,14 +453,14 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
     // previous solve's peer traffic from this one's); then the first halo push
     void *p0 = pb[d->epoch & 1];
     HB_CUDA(cudaMemcpyAsync(p0, x, es * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
-    if ((rc = hb_dist_halo_exchange(d, dtype, p0)) != HB_OK) return rc;
+    if ((rc = hb_dist_halo_exchange_nccl(d, dtype, p0)) != HB_OK) return rc;
     if ((rc = hb_spmv_internal(ctx, A, p0, Ap, nullptr)) != HB_OK) return rc;
     HB_DISPATCH(dtype, {
         cg_dstate<T> *st = (cg_dstate<T>*) state;
         dcg_setup_kernel<T><<<dgrid(ctx, n, DK_THREADS * 4), DK_THREADS, 0, ctx->stream>>>(n, st, tol, max_iter, (const T*) b, (const T*) Ap, (T*) r, (T*) p0,
                                                                                            ctx->partials, ctx->tickets + 6);
         HB_LAUNCH_CHECK(ctx);
-        if ((rc = hb_dist_allreduce_sum(d, dtype, &st->rr, 1)) != HB_OK) return rc;
+        if ((rc = hb_dist_allreduce_sum_nccl(d, dtype, &st->rr, 1)) != HB_OK) return rc;
         pcg_begin_kernel<T><<<HB_HALO_BLOCKS, DK_THREADS, 0, ctx->stream>>>(st, pv, d->epoch, d->send_idx, (const T*) p0);
         HB_LAUNCH_CHECK(ctx);
     });
@@ -606,7 +610,7 @@ int hb_dist_set_plan(hb_dist *d, int n_owned, int n_ghost, int nneigh, const int
     return HB_OK;
 }
 
-int hb_dist_halo_exchange(hb_dist *d, int dtype, void *x_ext){
+int hb_dist_halo_exchange_nccl(hb_dist *d, int dtype, void *x_ext){
     HB_ARG(d && (x_ext || d->n_owned + d->n_ghost == 0), "null");
     hb_ctx *ctx = d->ctx;
     if (d->neigh.empty()) return HB_OK;
@@ -631,10 +635,49 @@ int hb_dist_halo_exchange(hb_dist *d, int dtype, void *x_ext){
     return HB_OK;
 }
 
-int hb_dist_allreduce_sum(hb_dist *d, int dtype, void *dev_scalars, int count){
+int hb_dist_allreduce_sum_nccl(hb_dist *d, int dtype, void *dev_scalars, int count){
     HB_ARG(d && dev_scalars && count >= 0, "null");
     if (d->world == 1 || count == 0) return HB_OK;
     HB_NCCL(g_nccl.AllReduce(dev_scalars, dev_scalars, (size_t) count * reals_per_scalar(dtype), real_dtype(dtype), ncclSum, d->comm, d->ctx->stream));
+    return HB_OK;
+}
+
+// Public forms: over peer memory once the transport of the current plan is up for this element size (hb_dist_cg / hb_dist_gmres
+// bring it up collectively), over NCCL otherwise.
+int hb_dist_halo_exchange(hb_dist *d, int dtype, void *x_ext){
+    HB_ARG(d && (x_ext || d->n_owned + d->n_ghost == 0), "null");
+    const size_t es = hb_dtype_size(dtype);
+    if (!(d->peer_state == 1 && d->peer_es == es)) return hb_dist_halo_exchange_nccl(d, dtype, x_ext);
+    if (d->neigh.empty()) return HB_OK;
+    hb_ctx *ctx = d->ctx;
+    const unsigned long long g = d->epoch++;
+    char *pb = (char*) d->pbuf + HB_MAILBOX_BYTES + (size_t) (g & 1) * d->pbuf_ext_bytes;
+    HB_DISPATCH(dtype, {
+        peer_vec_push_kernel<T><<<HB_HALO_BLOCKS, 256, 0, ctx->stream>>>(d->pv_dev, g, d->send_idx, (const T*) x_ext);
+        ctx->launches++;
+        const int grid = dgrid(ctx, d->n_ghost, 256 * 4);
+        peer_vec_pull_kernel<T><<<grid, 256, 0, ctx->stream>>>(d->pv_dev, g, (const T*) pb + d->n_owned, (T*) x_ext + d->n_owned, d->n_ghost);
+    });
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_dist_allreduce_sum(hb_dist *d, int dtype, void *dev_scalars, int count){
+    HB_ARG(d && dev_scalars && count >= 0, "null");
+    if (d->world == 1 || count == 0) return HB_OK;
+    if (!(d->peer_state == 1 && count <= HB_PEER_VMAX)) return hb_dist_allreduce_sum_nccl(d, dtype, dev_scalars, count);
+    hb_ctx *ctx = d->ctx;
+    const unsigned long long v = d->vepoch++;
+    HB_DISPATCH(dtype, (peer_allsum_kernel<T><<<1, 128, 0, ctx->stream>>>(d->pv_dev, v, (T*) dev_scalars, count)));
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+// brings the peer transport up for this element size when it is available (collective); HB_OK either way unless something failed
+int hb_dist_prepare_transport(hb_dist *d, int dtype){
+    HB_ARG(d, "null");
+    if (d->world > 1 && d->world <= HB_MAX_PEERS && peer_env_enabled()){
+        int prc = peer_setup(d, hb_dtype_size(dtype));
+        if (prc != HB_OK && prc != HB_ERR_UNSUPPORTED) return prc;
+    }
     return HB_OK;
 }
 

@@ -20,14 +20,17 @@ static constexpr int HB_HALO_BLOCKS = 32;      // blocks that push the halo, eac
 static constexpr int HB_PEER_CH_PAP = 0, HB_PEER_CH_RR = 1;
 
 struct peer_slot { double v[2]; unsigned long long seq; unsigned long long pad; };              // 32 B
+static constexpr int HB_PEER_VMAX = 66;        // scalars per vector all-reduce (GMRES: restart <= 64 Gram-Schmidt coefficients + the norm)
+struct peer_vslot { double v[2 * HB_PEER_VMAX]; unsigned long long seq; unsigned long long pad; };
 // mailbox at the start of every rank's exchange buffer
 struct peer_mailbox {
     peer_slot slot[2][2][HB_MAX_PEERS];                             // [channel][epoch parity][source rank]
     unsigned long long halo_seq[HB_MAX_PEERS][HB_HALO_BLOCKS];      // [source rank][pushing block] = epoch + 1 of the last push
     int error;                                                      // set when a wait timed out (peer died / mis-sequenced)
     int pad[15];
+    peer_vslot vslot[2][HB_MAX_PEERS];                              // [vector-sum epoch parity][source rank]
 };
-static constexpr size_t HB_MAILBOX_BYTES = 8192;
+static constexpr size_t HB_MAILBOX_BYTES = 65536;
 static_assert(sizeof(peer_mailbox) <= HB_MAILBOX_BYTES, "mailbox layout");
 
 // what a kernel needs to reach its peers (lives in device memory, built by peer_setup)
@@ -148,4 +151,52 @@ __device__ __forceinline__ void peer_halo_push(const peer_view *pv, unsigned lon
     __syncthreads();
     if (threadIdx.x < pv->nneigh && pv->send_off[threadIdx.x + 1] > pv->send_off[threadIdx.x])
         st_release_sys(&pv->mail[pv->neigh[threadIdx.x]]->halo_seq[pv->rank][blockIdx.x], g + 1);
+}
+
+// In-place sum over ranks of `count` (<= HB_PEER_VMAX) scalars that live on the device: ONE block.  Every rank stores its values
+// into slot [v & 1][rank] of every peer's mailbox (v = number of this all-reduce, same on all ranks), releases a flag, waits for
+// the W flags in its own mailbox and adds the W vectors in rank order — the same bits on every rank.  Replaces ncclAllReduce for
+// the Gram-Schmidt coefficients of the row-partitioned GMRES (latency of one NVLink round trip instead of a collective launch).
+template<typename T>
+__global__ void __launch_bounds__(128) peer_allsum_kernel(const peer_view *pv, unsigned long long v, T *vec, int count){
+    const int W = pv->world, rank = pv->rank, t = threadIdx.x;
+    peer_mailbox *mine = pv->mail[rank];
+    if (t < count){
+        double a, b;
+        slot_pack<T>(vec[t], a, b);
+        for (int q = 0; q < W; q++){
+            volatile double *dst = pv->mail[q]->vslot[v & 1][rank].v;
+            dst[2 * t] = a; dst[2 * t + 1] = b;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < W) st_release_sys(&pv->mail[t]->vslot[v & 1][rank].seq, v + 1);
+    __shared__ int ok_s;
+    if (t == 0) ok_s = 1;
+    __syncthreads();
+    if (t < W && !peer_spin(&mine->vslot[v & 1][t].seq, v + 1)) ok_s = 0;
+    __syncthreads();
+    if (t < count){
+        double sa = 0.0, sb = 0.0;
+        for (int q = 0; q < W; q++){
+            sa += ld_volatile_f64(&mine->vslot[v & 1][q].v[2 * t]);
+            sb += ld_volatile_f64(&mine->vslot[v & 1][q].v[2 * t + 1]);
+        }
+        if (!ok_s) sa = sb = __longlong_as_double(0x7ff8000000000000LL);
+        vec[t] = slot_unpack<T>(sa, sb);
+    }
+    if (t == 0 && !ok_s) mine->error = 1;
+}
+// Halo of an arbitrary vector v_ext = [owned | ghosts] (GMRES basis vectors): push = our boundary entries into the neighbours' ghost
+// slots of exchange buffer (g & 1) + flags; pull = wait for the neighbours' flags, then copy our ghost slots behind the owned part.
+template<typename T>
+__global__ void __launch_bounds__(256) peer_vec_push_kernel(const peer_view *pv, unsigned long long g, const int * __restrict__ send_idx, const T * __restrict__ v){
+    peer_halo_push<T>(pv, g, [&](int j){ return v[send_idx[j]]; });
+}
+template<typename T>
+__global__ void __launch_bounds__(256) peer_vec_pull_kernel(const peer_view *pv, unsigned long long g, const T *ghost_src, T *ghost_dst, int n_ghost){
+    if (threadIdx.x < 32) peer_halo_wait(pv, g);
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ghost; i += gridDim.x * blockDim.x) ghost_dst[i] = ld_cg_T(ghost_src + i);
 }

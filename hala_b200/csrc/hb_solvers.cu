@@ -14,6 +14,7 @@
 hb_ctx* hb_dist_context(hb_dist *d);
 int hb_dist_owned(const hb_dist *d);
 int hb_dist_ghosts(const hb_dist *d);
+extern "C" int hb_dist_prepare_transport(hb_dist *d, int dtype);
 
 int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
 int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
@@ -272,6 +273,8 @@ int hb_dist_gmres(hb_dist *dist, const hb_csr *A, const void *b, void *x, double
     HB_ARG(restart >= 1, "restart must be positive");
     hb_ctx *ctx = hb_dist_context(dist);
     HB_ARG(A->rows == hb_dist_owned(dist) && A->cols == hb_dist_owned(dist) + hb_dist_ghosts(dist), "matrix shape does not match the exchange plan");
+    // halo of the basis vectors and the all-reduced Gram-Schmidt coefficients go over peer memory when the ranks can map each other
+    { int prc = hb_dist_prepare_transport(dist, A->dtype); if (prc != HB_OK) return prc; }
     HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, dist, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
     return HB_OK;
 }

@@ -20,6 +20,9 @@ DIST_SIGNATURES = {
     "hb_dist_set_plan": (_i, [_vp, _i, _i, _i, _pi, _pi, _pi, _vp]),
     "hb_dist_halo_exchange": (_i, [_vp, _i, _vp]),
     "hb_dist_allreduce_sum": (_i, [_vp, _i, _vp, _i]),
+    "hb_dist_halo_exchange_nccl": (_i, [_vp, _i, _vp]),
+    "hb_dist_allreduce_sum_nccl": (_i, [_vp, _i, _vp, _i]),
+    "hb_dist_prepare_transport": (_i, [_vp, _i]),
     "hb_dist_cg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi, C.POINTER(_d)]),
     "hb_dist_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "hb_dist_gmres": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _pi, C.POINTER(_d)]),

@@ -36,10 +36,17 @@ int hb_dist_transport(const hb_dist *dist, int *transport);
 int hb_dist_set_plan(hb_dist *dist, int n_owned, int n_ghost, int nneigh, const int *neigh,
                      const int *send_count, const int *recv_count, const int *send_idx_dev);
 
-/* x_ext = [x_owned | ghosts]: packs the requested owned entries, grouped ncclSend/ncclRecv, ghosts land in x_ext + n_owned */
+/* x_ext = [x_owned | ghosts]: the requested owned entries travel to the neighbours, ghosts land in x_ext + n_owned.  Over peer memory
+ * once that transport is up for the element size (two small kernels: push into the neighbours' exchange buffers + flags, then
+ * wait + copy), otherwise packed and sent with grouped ncclSend/ncclRecv (the *_nccl form always takes that route). */
 int hb_dist_halo_exchange(hb_dist *dist, int dtype, void *x_ext);
-/* in-place sum over ranks of `count` scalars of `dtype` that live on the device */
+int hb_dist_halo_exchange_nccl(hb_dist *dist, int dtype, void *x_ext);
+/* in-place sum over ranks of `count` scalars of `dtype` that live on the device: one block exchanging through the peers' mailboxes
+ * (count <= 66, summed in rank order: identical bits on all ranks), or ncclAllReduce */
 int hb_dist_allreduce_sum(hb_dist *dist, int dtype, void *dev_scalars, int count);
+int hb_dist_allreduce_sum_nccl(hb_dist *dist, int dtype, void *dev_scalars, int count);
+/* collective: brings the peer transport up for `dtype` when all ranks can map each other (hb_dist_cg / hb_dist_gmres call it) */
+int hb_dist_prepare_transport(hb_dist *dist, int dtype);
 
 /* Row-partitioned CG.  csr = local rows with columns renumbered to [owned | ghosts] (cols == n_owned + n_ghost);
  * b, x = owned parts.  Same recurrence, counter and stop test as hb_cg; per iteration: halo exchange of p, SpMV fused with

@@ -55,6 +55,11 @@ def main():
         want = os.environ.get("HB_EXPECT_TRANSPORT")
         if want:
             assert comm.transport() == want, (comm.transport(), want)
+        # --- the same SpMV again now that the transport of this plan is up (peer runs: halo pushed into the neighbours' exchange buffers)
+        x_ext[n_owned:] = 0
+        y.zero_()
+        comm.spmv(prob["A"], C.c_void_p(x_ext.data_ptr()), C.c_void_p(y.data_ptr()))
+        assert np.max(np.abs(y.cpu().numpy() - yref)) <= 1e-13 * scale, (name, rank, "spmv after cg")
         # --- a second solve from a non-zero initial guess (x0 halo over NCCL, epochs continue): converges in <= the first count
         x.copy_(torch.from_numpy(xo[lo:hi]).to(dev) * 0.5)
         it3, res3 = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tol, 10 ** 6)
