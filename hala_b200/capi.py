@@ -9,6 +9,7 @@ HB_F32, HB_F64, HB_C32, HB_C64 = 0, 1, 2, 3
 HB_OK = 0
 HB_POINTER_HOST, HB_POINTER_DEVICE = 0, 1
 HB_H2D, HB_D2H, HB_D2D = 0, 1, 2
+HB_TRANS_SCATTER, HB_TRANS_CHECKED, HB_TRANS_FROZEN = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -56,6 +57,9 @@ SIGNATURES = {
     "hb_spmv": (_i, [_vp, _vp, C.c_char, _vp, _vp, _vp, _vp]),
     "hb_spmv_dot": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hb_csr_set_variant": (_i, [_vp, _i]),
+    "hb_csr_set_transpose_mode": (_i, [_vp, _i]),
+    "hb_csr_values_changed": (_i, [_vp]),
+    "hb_csr_transpose_info": (_i, [_vp, _pi, _pi, C.POINTER(_sz)]),
     "hb_tri_create": (_i, [_vp, _i, C.c_char, C.c_char, _i, _i, _vp, _vp, _vp, _pvp]),
     "hb_tri_destroy": (_i, [_vp]),
     "hb_tri_info": (_i, [_vp, _pi, _pi, _pi]),

@@ -237,6 +237,12 @@ int hb_spmm(hb_ctx *ctx, const hb_csr *A, char transa, char transb, int b_rows, 
     if (M == 0 || N == 0) return HB_OK;
     HB_ARG(B && C, "null matrix");
     const size_t es = hb_dtype_size(A->dtype);
+    if (!an){       // op(A) = A^T / A^H: the same product with the cached CSR of A^T (hb_transpose.cu) when the object keeps one
+        const hb_csr *At = nullptr;
+        int rc = hb_csr_transposed(ctx, A, transa, &At);
+        if (rc != HB_OK) return rc;
+        if (At) return hb_spmm(ctx, At, 'N', transb, b_rows, b_cols, alpha, B, ldb, beta, C, ldc);
+    }
     // Fast path: right-hand sides in blocks of up to 8, interleaved (row-major) so that the operands of one non-zero are one
     // contiguous gather, through the streaming SpMV kernel in its multi right-hand-side mode: the matrix is read once per block.
     //   Bt = block of op(B), interleaved (interleave_kernel) -> Ct = A Bt (spmv_pipe_kernel<..., NBP>) -> C = alpha Ct + beta C (deinterleave_kernel)

@@ -39,6 +39,7 @@ static constexpr int    HB_NUM_TICKETS   = 64;
 static constexpr size_t HB_SCALAR_BYTES  = 4096;
 static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids never exceed this
 
+struct hb_tcache;                       // cached transposed copy behind op 'T' / 'C' (hb_transpose.cu)
 struct hb_csr {
     hb_ctx *ctx = nullptr;
     int dtype = HB_F64;
@@ -55,7 +56,12 @@ struct hb_csr {
     int  pipe_grid[2] = {0, 0};
     int  pipe_contiguous = 0;           // 1: contiguous equal-nnz pieces per CTA (cta_rows table); 0: round-robin tile sweep
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
+    hb_tcache *tc = nullptr;            // transpose mode + (lazily built) CSR of A^T; owned
 };
+hb_tcache* hb_tcache_new();
+void hb_tcache_delete(hb_tcache *tc);
+// op 'N' matrix standing for op(A), op = 'T' / 'C', with up-to-date values; *out = nullptr: use the scatter kernel
+int hb_csr_transposed(hb_ctx *ctx, const hb_csr *A, char trans, const hb_csr **out);
 
 void hb_set_error(const std::string &msg);
 int  hb_cuda_fail(cudaError_t e, const char *what);

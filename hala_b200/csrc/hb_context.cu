@@ -1,8 +1,13 @@
 // hb_context.cu — context, error plumbing and device memory of libhalab200.
 // Replaces: gpu_engine handle management (reference gpu/hala_gpu_engine.hpp:60-163), gpu_allocate/gpu_free/gpu_copy_n
 // (gpu/hala_cuda_common.hpp:253-330), gpu_vector::fill (gpu/hala_gpu_vector.hpp:147-156), set_zero (gpu_engine.hpp:335-352).
+// Device memory comes from the driver's stream-ordered pool (cudaMallocAsync / cudaFreeAsync with the release threshold lifted), so
+// the load -> operation -> unload pattern of mixed_engine and binded_gpu_vector (wax/hala_lib_extensions.hpp:126-241,
+// gpu/hala_gpu_vector.hpp:224-249) and every new_vector / resize stop paying a cudaMalloc plus a device-synchronising cudaFree per
+// call: a freed block is handed out again without touching the OS.  HB_MEM_POOL=0 restores cudaMalloc/cudaFree.
 #include "hb_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 static thread_local std::string g_last_error;
 
@@ -10,6 +15,62 @@ void hb_set_error(const std::string &msg){ g_last_error = msg; }
 int hb_cuda_fail(cudaError_t e, const char *what){
     g_last_error = std::string(what) + " failed with message: " + cudaGetErrorString(e);
     return HB_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ pooled device memory
+static constexpr int HB_MAX_DEVICES = 64;
+static bool g_pool_ready[HB_MAX_DEVICES];
+static bool g_custom_stream[HB_MAX_DEVICES];     // a context of this device runs on a caller-supplied stream
+static bool pool_enabled(){
+    static int v = -1;
+    if (v < 0){ const char *e = getenv("HB_MEM_POOL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+static void pool_trim(int device){
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+}
+// the current device is `device`
+static cudaError_t pool_malloc(int device, void **ptr, size_t bytes, cudaStream_t stream){
+    if (!pool_enabled() || device < 0 || device >= HB_MAX_DEVICES) return cudaMalloc(ptr, bytes);
+    if (!g_pool_ready[device]){
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess){
+            unsigned long long keep = ~0ull;                // never give freed blocks back to the OS on a synchronisation
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        g_pool_ready[device] = true;
+    }
+    cudaError_t e = cudaMallocAsync(ptr, bytes, stream);
+    if (e != cudaSuccess){                                   // pool exhausted or unsupported: give the cache back and ask the plain allocator
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        pool_trim(device);
+        return cudaMalloc(ptr, bytes);
+    }
+    // an allocation is ordered on `stream`; contexts on other non-blocking streams may touch it at once, so make it visible to all
+    if (g_custom_stream[device]) e = cudaStreamSynchronize(stream);
+    return e;
+}
+static cudaError_t pool_free(void *ptr, cudaStream_t stream){
+    if (!pool_enabled()) return cudaFree(ptr);
+    cudaPointerAttributes attr;
+    int cur = 0;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice || cudaGetDevice(&cur) != cudaSuccess){
+        cudaGetLastError();
+        return cudaFree(ptr);
+    }
+    const int dev = attr.device;
+    if (dev != cur){ cudaSetDevice(dev); stream = nullptr; }
+    // cudaFree synchronises the device, which is what protects a block still in use on another stream; keep that when a caller
+    // brought its own stream, otherwise the legacy default stream orders the free after all work of the blocking streams
+    if (dev >= 0 && dev < HB_MAX_DEVICES && g_custom_stream[dev]) cudaDeviceSynchronize();
+    cudaError_t e = cudaFreeAsync(ptr, stream);
+    if (e != cudaSuccess){ cudaGetLastError(); e = cudaFree(ptr); }
+    if (dev != cur) cudaSetDevice(cur);
+    return e;
 }
 
 template<typename T> __global__ void fill_kernel(size_t n, T value, T *x){
@@ -78,10 +139,16 @@ int hb_ctx_destroy(hb_ctx *ctx){
 int hb_ctx_trim(hb_ctx *ctx){
     HB_ARG(ctx, "ctx is null");
     if (ctx->work){ HB_CUDA(cudaFree(ctx->work)); ctx->work = nullptr; ctx->work_bytes = 0; }
+    if (pool_enabled()){ HB_CUDA(cudaDeviceSynchronize()); pool_trim(ctx->device); }     // and the blocks the memory pool keeps
     return HB_OK;
 }
 int hb_ctx_device(const hb_ctx *ctx, int *device){ HB_ARG(ctx && device, "null"); *device = ctx->device; return HB_OK; }
-int hb_ctx_set_stream(hb_ctx *ctx, void *s){ HB_ARG(ctx, "ctx is null"); ctx->stream = (cudaStream_t) s; return HB_OK; }
+int hb_ctx_set_stream(hb_ctx *ctx, void *s){
+    HB_ARG(ctx, "ctx is null");
+    ctx->stream = (cudaStream_t) s;
+    if (s && ctx->device >= 0 && ctx->device < HB_MAX_DEVICES) g_custom_stream[ctx->device] = true;
+    return HB_OK;
+}
 int hb_ctx_get_stream(const hb_ctx *ctx, void **s){ HB_ARG(ctx && s, "null"); *s = (void*) ctx->stream; return HB_OK; }
 int hb_ctx_sync(hb_ctx *ctx){
     HB_ARG(ctx, "ctx is null");
@@ -116,13 +183,12 @@ int hb_malloc(hb_ctx *ctx, size_t bytes, void **ptr){
     HB_CUDA(cudaSetDevice(ctx->device));      // as gpu_allocate does (gpu/hala_cuda_common.hpp:255)
     *ptr = nullptr;
     if (bytes == 0) return HB_OK;
-    cudaError_t e = cudaMalloc(ptr, bytes);
+    cudaError_t e = pool_malloc(ctx->device, ptr, bytes, ctx->stream);
     if (e != cudaSuccess){ hb_cuda_fail(e, "hb_malloc"); return HB_ERR_ALLOC; }
     return HB_OK;
 }
 int hb_free(hb_ctx *ctx, void *ptr){
-    (void) ctx;
-    if (ptr) HB_CUDA(cudaFree(ptr));
+    if (ptr) HB_CUDA(pool_free(ptr, ctx ? ctx->stream : nullptr));
     return HB_OK;
 }
 static cudaMemcpyKind to_kind(int kind){
@@ -165,11 +231,11 @@ int hb_dev_malloc(int device, size_t bytes, void **ptr){
     HB_CUDA(cudaSetDevice(device));
     *ptr = nullptr;
     if (bytes == 0) return HB_OK;
-    cudaError_t e = cudaMalloc(ptr, bytes);
+    cudaError_t e = pool_malloc(device, ptr, bytes, nullptr);
     if (e != cudaSuccess){ hb_cuda_fail(e, "hb_dev_malloc"); return HB_ERR_ALLOC; }
     return HB_OK;
 }
-int hb_dev_free(void *ptr){ if (ptr) HB_CUDA(cudaFree(ptr)); return HB_OK; }
+int hb_dev_free(void *ptr){ if (ptr) HB_CUDA(pool_free(ptr, nullptr)); return HB_OK; }
 int hb_dev_memcpy(void *dst, const void *src, size_t bytes, int kind){
     if (bytes == 0) return HB_OK;
     HB_CUDA(cudaMemcpy(dst, src, bytes, to_kind(kind)));

@@ -15,7 +15,8 @@
 //   * row-vector ("sub-warp / warp per row"): TPR lanes per row, strided walk, shuffle reduction; used for matrices
 //       whose mean row is long, and as the unaligned fallback.
 // Both fuse an optional <x, y> dot (conjugated) into the same pass for CG (hb_spmv_dot).
-// op 'T' / 'C': y = beta y, then atomic scatter y[col] += alpha x[row] op(val) (first cut).
+// op 'T' / 'C': the op 'N' kernels on a cached CSR of A^T (hb_transpose.cu); in scatter mode y = beta y, then
+//   atomic scatter y[col] += alpha x[row] op(val).
 #include "hb_common.cuh"
 #include "hb_spmv_pipe.cuh"
 #include <algorithm>
@@ -468,6 +469,7 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     A->ctx = ctx; A->dtype = dtype; A->rows = rows; A->cols = cols; A->nnz = nnz;
     A->pntr = pntr; A->indx = indx; A->vals = vals;
     A->vec_aligned = aligned16p(indx) && aligned16p(vals);
+    A->tc = hb_tcache_new();
     A->mean_row_nnz = rows > 0 ? (double) nnz / rows : 0.0;
     // one-time analysis: longest row (decides nothing structural today beyond reporting, but costs one tiny kernel)
     A->stats_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048);
@@ -512,6 +514,7 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
 int hb_csr_destroy(hb_csr *csr){
     if (!csr) return HB_OK;
     for (int c = 0; c < 2; c++) if (csr->cta_rows[c]) cudaFree(csr->cta_rows[c]);
+    hb_tcache_delete(csr->tc);
     delete csr;
     return HB_OK;
 }
@@ -536,9 +539,13 @@ int hb_spmv(hb_ctx *ctx, const hb_csr *A, char trans, const void *alpha, const v
     if (ny == 0) return HB_OK;
     HB_ARG(y, "y is null");
     HB_ARG(x || (hb_is_n(trans) ? A->cols : A->rows) == 0, "x is null");
+    // op 'T' / 'C': the op 'N' kernel on the cached CSR of A^T (hb_transpose.cu) unless the object is in scatter mode
+    const hb_csr *At = nullptr;
+    if (!hb_is_n(trans)){ int rc = hb_csr_transposed(ctx, A, trans, &At); if (rc != HB_OK) return rc; }
     HB_DISPATCH(A->dtype, {
         scalar_arg<T> a = make_scalar<T>(ctx, alpha), b = make_scalar<T>(ctx, beta);
         if (hb_is_n(trans)) return hb_spmv_n_typed<T, false>(ctx, A, (const T*) x, (T*) y, a, b, nullptr, nullptr);
+        if (At) return hb_spmv_n_typed<T, false>(ctx, At, (const T*) x, (T*) y, a, b, nullptr, nullptr);
         int grid = hb_grid_for(ctx, (size_t) ny, 256, 8);
         scale_or_zero_kernel<T><<<grid, 256, 0, ctx->stream>>>(ny, b, (T*) y);
         HB_LAUNCH_CHECK(ctx);

@@ -304,6 +304,20 @@ class gpu_sparse_matrix:
     def set_variant(self, variant):
         check(lib.hb_csr_set_variant(self.h, int(variant)), "hb_csr_set_variant")
 
+    def set_transpose_mode(self, mode):
+        """how op 'T'/'C' products treat the cached CSR of A^T: 'checked' (default), 'frozen', 'scatter' (halab200.h)"""
+        code = {"scatter": 0, "checked": 1, "frozen": 2}.get(mode, mode)
+        check(lib.hb_csr_set_transpose_mode(self.h, int(code)), "hb_csr_set_transpose_mode")
+
+    def values_changed(self):
+        """tell a 'frozen' matrix that the caller rewrote the value array"""
+        check(lib.hb_csr_values_changed(self.h), "hb_csr_values_changed")
+
+    def transpose_info(self):
+        m, b, n = C.c_int(0), C.c_int(0), C.c_size_t(0)
+        check(lib.hb_csr_transpose_info(self.h, C.byref(m), C.byref(b), C.byref(n)), "hb_csr_transpose_info")
+        return {"mode": ("scatter", "checked", "frozen")[m.value], "built": bool(b.value), "bytes": n.value}
+
     def max_row_nnz(self):
         m = C.c_int(0)
         check(lib.hb_csr_info(self.h, None, None, None, None, C.byref(m)), "hb_csr_info")
@@ -437,7 +451,9 @@ def make_sparse_matrix(engine, *args):
 
 def sparse_gemv(engine, trans, M, N, alpha, pntr, indx, vals, x, beta, y):
     """One-shot SpMV (gpu/hala_cuda_sparse_general.hpp:407-419): builds a temporary matrix view per call."""
-    make_sparse_matrix(engine, M, N, indx.size(), pntr, indx, vals).gemv(trans, alpha, x, beta, y)
+    A = make_sparse_matrix(engine, M, N, indx.size(), pntr, indx, vals)
+    A.set_transpose_mode("scatter")     # a view that lives for one product: building the transposed copy cannot pay off
+    A.gemv(trans, alpha, x, beta, y)
 
 
 # ---------------------------------------------------------------- solvers (identity preconditioner)

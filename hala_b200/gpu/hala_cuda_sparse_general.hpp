@@ -50,6 +50,10 @@ public:
 
     gpu_engine const& engine() const{ return rengine; }
     hb_csr* csr() const{ return handle; }
+    //! extension: how op 'T'/'C' products use the cached CSR of the transpose (HB_TRANS_CHECKED default, HB_TRANS_FROZEN, HB_TRANS_SCATTER; halab200.h)
+    void set_transpose_mode(int mode) const{ check_hb(hb_csr_set_transpose_mode(handle, mode), "hala::gpu_sparse_matrix::set_transpose_mode()"); }
+    //! extension: tell a HB_TRANS_FROZEN matrix that the value array was rewritten
+    void values_changed() const{ check_hb(hb_csr_values_changed(handle), "hala::gpu_sparse_matrix::values_changed()"); }
 
     template<typename FPa, class VectorLikeX, typename FPb, class VectorLikeY>
     size_t gemv_buffer_size(char trans, FPa, VectorLikeX const&, FPb beta, VectorLikeY &&y) const{
@@ -132,7 +136,9 @@ void sparse_gemv(gpu_engine const &engine, char trans, int M, int N,
     engine.check_gpu(pntr, indx, vals, x, y);
     pntr_check_set_size(beta, y, (is_n(trans)) ? M : N, 1);
     assert( valid::sparse_gemv(trans, M, N, 0, pntr, indx, vals, x, y) );
-    make_sparse_matrix(engine, M, N, get_size_int(indx), pntr, indx, vals).gemv(trans, alpha, x, beta, y);
+    auto matrix = make_sparse_matrix(engine, M, N, get_size_int(indx), pntr, indx, vals);
+    matrix.set_transpose_mode(HB_TRANS_SCATTER);      // a view that lives for one product: building the transposed copy cannot pay off
+    matrix.gemv(trans, alpha, x, beta, y);
 }
 
 //! One-shot SpMM (reference :444-457): a temporary view per call.
@@ -146,8 +152,9 @@ void sparse_gemm(gpu_engine const &engine, char transa, char transb, int M, int 
     pntr_check_set_size(beta, C, ldc, N);
     int nnz = get_size_int(indx);
     assert( valid::sparse_gemm(transa, transb, M, N, K, nnz, pntr, indx, vals, B, ldb, C, ldc) );
-    make_sparse_matrix(engine, (is_n(transa)) ? M : K, (is_n(transa)) ? K : M, nnz, pntr, indx, vals)
-        .gemm(transa, transb, (is_n(transb)) ? K : N, (is_n(transb)) ? N : K, alpha, B, ldb, beta, C, ldc);
+    auto matrix = make_sparse_matrix(engine, (is_n(transa)) ? M : K, (is_n(transa)) ? K : M, nnz, pntr, indx, vals);
+    if (N < 8) matrix.set_transpose_mode(HB_TRANS_SCATTER);     // one-product view: the transposed copy pays off only over many columns
+    matrix.gemm(transa, transb, (is_n(transb)) ? K : N, (is_n(transb)) ? N : K, alpha, B, ldb, beta, C, ldc);
 }
 
 }

@@ -90,6 +90,18 @@ int hb_spmv_dot(hb_ctx *ctx, const hb_csr *csr, const void *x, void *y, void *do
 /* selects the SpMV kernel variant for op 'N': 0 = auto, 1 = row-vector (sub-warp per row), 2 = staged tiles (LDG),
  * 3 = staged tiles (TMA bulk copy pipeline).  For benchmarking; auto is what the header layer uses. */
 int hb_csr_set_variant(hb_csr *csr, int variant);
+/* op 'T' / 'C' products (cusparseSpMV with a transposed operation, :264-277; pinned by tests/sparse_tests.hpp:184-190) run the op 'N'
+ * kernel on a CSR of A^T that the object builds on the device at its first such product and keeps (nnz * (8 + sizeof value) + 4 cols
+ * bytes).  The object is a non-owning view whose values the caller may change between products (:186-190), hence the mode:
+ *   HB_TRANS_CHECKED (default) a 64-bit fingerprint pass over the value array per product, values re-gathered when it changed
+ *   HB_TRANS_FROZEN            no check: the caller reports changes with hb_csr_values_changed()
+ *   HB_TRANS_SCATTER           no cached copy: atomic scatter in the caller's row order (also the fallback when the copy does not fit)
+ * The structure arrays (pntr, indx) are taken as fixed for the life of the object.  HB_TRANS_MODE=scatter|checked|frozen sets the
+ * default of new objects. */
+enum { HB_TRANS_SCATTER = 0, HB_TRANS_CHECKED = 1, HB_TRANS_FROZEN = 2 };
+int hb_csr_set_transpose_mode(hb_csr *csr, int mode);
+int hb_csr_values_changed(hb_csr *csr);
+int hb_csr_transpose_info(const hb_csr *csr, int *mode, int *built, size_t *bytes);
 
 /* ---- sparse triangular solves and ILU(0): gpu_triangular_matrix (gpu/hala_cuda_sparse_triangular.hpp:38-454 ->
  *      cusparseSpSV / cusparseSpSM) and gpu_ilu (gpu/hala_gpu_ilu.hpp:45-199 -> cusparse?csrilu02 + two triangular solves) ----
