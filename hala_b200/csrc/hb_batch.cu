@@ -8,10 +8,13 @@
 // The wax templates batch_dot / batch_axpy / batch_scal / batch_max_norm2 / vdivide (wax/hala_blas_extensions.hpp:203-275,353-365)
 // are built from exactly these plus gemv('T'), axpy, vcopy, iamax and norm2, so solve_batch_cg runs unchanged on top.
 #include "hb_common.cuh"
+#include <cstdlib>
 
 static constexpr int BT_THREADS = 256;
 
 bool hb_spmm_interleaved_ok(const hb_csr *A);
+bool hb_spmm_lpc_ok(const hb_csr *A, int nbp);
+int  hb_spmm_lpc(hb_ctx *ctx, const hb_csr *A, int nbp, int nb, const void *B, size_t sxr, size_t sxc, const void *alpha, const void *beta, void *Cm, size_t ldc);
 int  hb_spmm_interleaved(hb_ctx *ctx, const hb_csr *A, int nbp, const void *Bt, size_t ldbt, void *Ct, size_t ldct);
 
 // ------------------------------------------------------------------------------------------------ SpMM, op(A) = A
@@ -247,7 +250,24 @@ int hb_spmm(hb_ctx *ctx, const hb_csr *A, char transa, char transb, int b_rows, 
     // contiguous gather, through the streaming SpMV kernel in its multi right-hand-side mode: the matrix is read once per block.
     //   Bt = block of op(B), interleaved (interleave_kernel) -> Ct = A Bt (spmv_pipe_kernel<..., NBP>) -> C = alpha Ct + beta C (deinterleave_kernel)
     const bool bconj = hb_is_c(transb) && (A->dtype == HB_C32 || A->dtype == HB_C64);
-    if (an && A->nnz > 0 && hb_spmm_interleaved_ok(A) && !(bconj && !bn)){
+    // Alternative form of the streaming kernel, "lane per column" (HB_SPMM_PATH=lpc): B and C used where they lie, NBP adjacent lanes share a
+    // row, no interleaving passes, no workspace, rows summed left to right.  Measured on B200 it loses to the interleaved form on long rows
+    // (27-point 128^3, 4 columns: 340 us against 272 us) and ties on short ones (7-point 256^3: 828 us against 838 us): both are bound by the
+    // L1TEX data stage at about one wavefront per gathered sector (ncu: l1tex data-pipe 87 %, DRAM 28-44 %), see DESIGN.md §4c.
+    static const char *path_env = getenv("HB_SPMM_PATH");
+    if (an && A->nnz > 0 && path_env && path_env[0] == 'l' && !(bconj && !bn) && hb_spmm_lpc_ok(A, 4)){
+        int rc = HB_OK;
+        for (int n0 = 0; n0 < N && rc == HB_OK; n0 += 4){
+            const int nb = (N - n0 < 4) ? (N - n0) : 4;
+            // op(B)[c][n]: transb N -> B[c + n ldb]; otherwise B[n + c ldb]
+            const char *Bblk = (const char*) B + es * (bn ? (size_t) n0 * (size_t) ldb : (size_t) n0);
+            rc = hb_spmm_lpc(ctx, A, 4, nb, Bblk, bn ? (size_t) 1 : (size_t) ldb, bn ? (size_t) ldb : (size_t) 1, alpha, beta,
+                             (char*) C + es * (size_t) n0 * (size_t) ldc, (size_t) ldc);
+        }
+        return rc;
+    }
+    const bool want_il = !path_env || path_env[0] != 'g';
+    if (an && A->nnz > 0 && want_il && hb_spmm_interleaved_ok(A) && !(bconj && !bn)){
         const int saved_mode = ctx->pointer_mode;
         int rc = HB_OK;
         void *arena = nullptr;

@@ -319,7 +319,7 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                                             A->pipe_contiguous ? A->cta_rows[CFG] : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip,
                                                             (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols,
-                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0);
+                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0, (size_t) 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -349,7 +349,7 @@ static int launch_pipe_mm_cfg(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t 
     scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
     scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, Bt, Ct, one, zero,
-                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct);
+                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct, (size_t) 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -363,7 +363,61 @@ static int launch_pipe_mm(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t ldbt
         default: return launch_pipe_mm_cfg<T, CFG, 1, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
     }
 }
+// ---- multi right-hand-side product, lane-per-column form (spmv_pipe_kernel<..., NBP, LPC = true>): B and C used where they lie
+static int pipe_mm_tpr(const hb_csr *A, int nbp){
+    const int t = pipe_tpr(A->mean_row_nnz, hb_dtype_size(A->dtype));
+    return t > nbp ? nbp : t;
+}
+template<typename T, int CFG, int TPR, int NBP>
+static int launch_pipe_lpc_cfg(hb_ctx *ctx, const hb_csr *A, int nb, const T *B, size_t sxr, size_t sxc, scalar_arg<T> alpha, scalar_arg<T> beta, T *Cm, size_t ldc){
+    using C = pipe_cfg<CFG>;
+    const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, false, NBP, true>;
+    static int occ = -1;
+    if (occ < 0){
+        HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int n = 0;
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::THREADS, smem));
+        occ = n < 1 ? 1 : n;
+    }
+    const int tile_rows = C::THREADS / TPR;
+    const long long ntiles = ((long long) A->rows + tile_rows - 1) / tile_rows;
+    const int grid = (int) std::min<long long>(ntiles, (long long) ctx->num_sms * occ);
+    k<<<grid, C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, B, Cm, alpha, beta,
+                                               nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, nb, A->cols, nullptr, 0ull, sxr, ldc, sxc);
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+template<typename T, int CFG, int NBP>
+static int launch_pipe_lpc(hb_ctx *ctx, const hb_csr *A, int nb, const T *B, size_t sxr, size_t sxc, scalar_arg<T> alpha, scalar_arg<T> beta, T *Cm, size_t ldc){
+    switch (pipe_mm_tpr(A, NBP)){
+        case 4:  return launch_pipe_lpc_cfg<T, CFG, 4, NBP>(ctx, A, nb, B, sxr, sxc, alpha, beta, Cm, ldc);
+        case 2:  return launch_pipe_lpc_cfg<T, CFG, 2, NBP>(ctx, A, nb, B, sxr, sxc, alpha, beta, Cm, ldc);
+        default: return launch_pipe_lpc_cfg<T, CFG, 1, NBP>(ctx, A, nb, B, sxr, sxc, alpha, beta, Cm, ldc);
+    }
+}
 int hb_spmv_variant(const hb_csr *A);
+// can the lane-per-column streaming kernel take this matrix with blocks of nbp right-hand sides?  (every tile fits its stage)
+bool hb_spmm_lpc_ok(const hb_csr *A, int nbp){
+    if (hb_spmv_variant(A) != 3) return false;
+    const size_t es = hb_dtype_size(A->dtype);
+    const int threads = A->pipe_cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
+    const int rows_per_tile = threads / pipe_mm_tpr(A, nbp);
+    const long long cap = (long long) threads * (es == 16 ? 4 : 8);
+    return (long long) rows_per_tile * A->max_row_nnz + 4 <= cap;
+}
+// C[:, 0..nb) = alpha A op(B)[:, 0..nb) + beta C, nb <= nbp (= 4); operand (c, kb) at B[c * sxr + kb * sxc]; alpha / beta host or device
+// pointers according to the pointer mode
+int hb_spmm_lpc(hb_ctx *ctx, const hb_csr *A, int nbp, int nb, const void *B, size_t sxr, size_t sxc, const void *alpha, const void *beta, void *Cm, size_t ldc){
+    HB_DISPATCH(A->dtype, {
+        scalar_arg<T> a = make_scalar<T>(ctx, alpha), b = make_scalar<T>(ctx, beta);
+        HB_ARG(nbp == 4, "lane-per-column blocks are 4 wide (8-wide measured 1.5x slower per column on B200)");
+        if (A->pipe_cfg == 0) return launch_pipe_lpc<T, 0, 4>(ctx, A, nb, (const T*) B, sxr, sxc, a, b, (T*) Cm, ldc);
+        return launch_pipe_lpc<T, 1, 4>(ctx, A, nb, (const T*) B, sxr, sxc, a, b, (T*) Cm, ldc);
+    });
+    return HB_OK;
+}
 // can the interleaved streaming kernel take this matrix?  (pipeline available, every tile fits its stage, no warp / CTA rows)
 bool hb_spmm_interleaved_ok(const hb_csr *A){
     if (hb_spmv_variant(A) != 3) return false;

@@ -45,12 +45,19 @@ __global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int til
 // ("interleaved") block Bt[col * ldx + kb], kb < NBP, so the NBP operands of one non-zero are ONE contiguous 128-bit-packet gather,
 // and y the interleaved result Ct[row * ldy + kb]; the matrix stream is shared by all NBP right-hand sides.  The host only
 // launches it when every tile fits its stage and no row is long enough for the warp / CTA paths.
-template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0>
+// LPC ("lane per column", with NBP > 0): x and y are used where they lie — operand of non-zero (i, c) for right-hand side kb is
+// x[c * ldx + kb * sxc], result y[i + kb * ldy] = alpha sum + beta y — and NBP adjacent lanes share one row, lane kb owning right-hand
+// side kb: the NBP operands of a non-zero are one warp-level request of NBP adjacent lanes, adjacent rows (adjacent lane groups) gather
+// adjacent columns, so one request touches 2-3 lines instead of one line per lane (the packet-per-lane form above is bound by the
+// L1TEX tag stage: ncu 88 % l1tex, 44 % DRAM on the 27-point matrix), no shuffle reduction, and every row is summed left to right
+// exactly as the reference does.  A tile of ROWS = THREADS / TPR rows is walked by THREADS / NBP groups, NBP / TPR rows each; `xpf`
+// carries the number of live right-hand sides of this block (lanes beyond it compute on column 0 and store nothing).
+template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0, bool LPC = false>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
                                                             void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
-                                                            const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy){
+                                                            const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy, size_t sxc){
     constexpr int ROWS = THREADS / TPR;
     constexpr int CAP  = THREADS * pipe_slots<T>();
     constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
@@ -157,7 +164,39 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             int rs = 0, re = 0;
             if (myrow < rows){ rs = sp[grp]; re = sp[grp + 1]; }
             T sum = zero_of<T>();
-            if constexpr (NBP > 0){
+            if constexpr (NBP > 0 && LPC){
+                constexpr int GROUPS = THREADS / NBP, RPG = ROWS / GROUPS, MU = (sizeof(T) == 16 ? 4 : 8);
+                static_assert(NBP >= TPR && ROWS % GROUPS == 0 && RPG >= 1, "a tile must be whole passes of the lane groups");
+                const int kb = tid % NBP, g = tid / NBP;
+                const bool live = kb < xpf;
+                const T *sv = stage_vals(s); const int *sc = stage_cols(s);
+                const T *xk = x + (live ? (size_t) kb * sxc : (size_t) 0);
+                #pragma unroll 1
+                for (int rr = 0; rr < RPG; rr++){
+                    const int lr = g + rr * GROUPS, row = r0 + lr;
+                    if (row >= rows) break;
+                    const int ls = sp[lr] - a0, le = sp[lr + 1] - a0;
+                    T acc = zero_of<T>();
+                    for (int base = ls; base < le; base += MU){
+                        int c[MU]; T v[MU], xv[MU];
+                        #pragma unroll
+                        for (int u = 0; u < MU; u++) if (base + u < le){ c[u] = sc[base + u]; v[u] = sv[base + u]; }
+                        #pragma unroll
+                        for (int u = 0; u < MU; u++) if (base + u < le) xv[u] = ld_ro(xk + (size_t) c[u] * ldx);
+                        #pragma unroll
+                        for (int u = 0; u < MU; u++) if (base + u < le) acc = hfma(v[u], xv[u], acc);
+                    }
+                    if (live){
+                        T *cp = y + (size_t) row + (size_t) kb * ldy;
+                        T out = hmul(alpha, acc);
+                        if (use_beta) out = hfma(beta, *cp, out);
+                        *cp = out;
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+            if constexpr (NBP > 0 && !LPC){
                 constexpr int NV = vec16<T>::N, NPK = NBP / NV, MU = (NPK >= 4 ? 2 : 4);    // packets per entry; entries per lane in flight
                 static_assert(NBP % NV == 0, "interleaved block must be whole 128-bit packets");
                 T sums[NBP];
