@@ -56,6 +56,7 @@ struct hb_csr {
     int  pipe_grid[2] = {0, 0};
     int  pipe_contiguous = 0;           // 1: contiguous equal-nnz pieces per CTA (cta_rows table); 0: round-robin tile sweep
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
+    int  tpr = 1;                       // lanes per row of the streaming kernel: from the mean row length, one notch up for heavy-tailed rows
     hb_tcache *tc = nullptr;            // transpose mode + (lazily built) CSR of A^T; owned
 };
 hb_tcache* hb_tcache_new();

@@ -298,19 +298,11 @@ static size_t pipe_smem_bytes(int threads, int tpr, int stages, size_t es){
     return stages * ((cap + 4) * (es + sizeof(int)) + (rows + 4) * sizeof(int));
 }
 // lanes per row: the smallest power of two that keeps a typical row within ~7 entries per lane (<= two batches of four)
+static constexpr int HB_HEAVY_TPR_SHIFT = 0;     // notches added to lanes-per-row for heavy-tailed matrices (HB_PIPE_TPR_SHIFT overrides)
 static int pipe_tpr(double mean, size_t es){
     const double slots = es == 16 ? 4.0 : 8.0;
     return mean > 7.5 * slots ? 16 : mean > 3.75 * slots ? 8 : mean > 1.9 * slots ? 4 : mean > 0.94 * slots ? 2 : 1;
 }
-static int pipe_ctas_per_sm(int cfg, double mean, int dtype){
-    const int threads = cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS, stages = cfg == 0 ? pipe_cfg<0>::STAGES : pipe_cfg<1>::STAGES;
-    const size_t smem = pipe_smem_bytes(threads, pipe_tpr(mean, hb_dtype_size(dtype)), stages, hb_dtype_size(dtype));
-    int by_smem = (int) ((227 * 1024) / (smem + 1024 + 512));        // + per-CTA reservation + static shared
-    int by_thr = threads >= 256 ? 3 : 6;                              // __launch_bounds__ minBlocks of the kernel (register budget)
-    int n = by_smem < by_thr ? by_smem : by_thr;
-    return n < 1 ? 1 : n;
-}
-
 template<typename T, int CFG, int TPR, bool DOT>
 static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
     using C = pipe_cfg<CFG>;
@@ -325,7 +317,7 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
 }
 template<typename T, int CFG, bool DOT>
 static int launch_pipe(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
-    switch (pipe_tpr(A->mean_row_nnz, sizeof(T))){
+    switch (A->tpr){
         case 16: return launch_pipe_cfg<T, CFG, 16, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         case 8:  return launch_pipe_cfg<T, CFG, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         case 4:  return launch_pipe_cfg<T, CFG, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
@@ -355,7 +347,7 @@ static int launch_pipe_mm_cfg(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t 
 }
 template<typename T, int CFG, int NBP>
 static int launch_pipe_mm(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t ldbt, T *Ct, size_t ldct){
-    switch (pipe_tpr(A->mean_row_nnz, sizeof(T))){
+    switch (A->tpr){
         case 16: return launch_pipe_mm_cfg<T, CFG, 16, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
         case 8:  return launch_pipe_mm_cfg<T, CFG, 8, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
         case 4:  return launch_pipe_mm_cfg<T, CFG, 4, NBP>(ctx, A, Bt, ldbt, Ct, ldct);
@@ -365,7 +357,7 @@ static int launch_pipe_mm(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t ldbt
 }
 // ---- multi right-hand-side product, lane-per-column form (spmv_pipe_kernel<..., NBP, LPC = true>): B and C used where they lie
 static int pipe_mm_tpr(const hb_csr *A, int nbp){
-    const int t = pipe_tpr(A->mean_row_nnz, hb_dtype_size(A->dtype));
+    const int t = A->tpr;
     return t > nbp ? nbp : t;
 }
 template<typename T, int CFG, int TPR, int NBP>
@@ -423,7 +415,7 @@ bool hb_spmm_interleaved_ok(const hb_csr *A){
     if (hb_spmv_variant(A) != 3) return false;
     const size_t es = hb_dtype_size(A->dtype);
     const int threads = A->pipe_cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
-    const int rows_per_tile = threads / pipe_tpr(A->mean_row_nnz, es);
+    const int rows_per_tile = threads / A->tpr;
     const long long cap = (long long) threads * (es == 16 ? 4 : 8);
     return A->max_row_nnz < PIPE_WARPROW && (long long) rows_per_tile * A->max_row_nnz + 4 <= cap;
 }
@@ -525,7 +517,7 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     A->vec_aligned = aligned16p(indx) && aligned16p(vals);
     A->tc = hb_tcache_new();
     A->mean_row_nnz = rows > 0 ? (double) nnz / rows : 0.0;
-    // one-time analysis: longest row (decides nothing structural today beyond reporting, but costs one tiny kernel)
+    // one-time analysis: longest row (one tiny kernel, one 4-byte read-back) — decides the tile shape and the tile-to-CTA map below
     A->stats_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048);
     HB_CUDA(cudaMemsetAsync(A->stats_dev, 0, sizeof(int), ctx->stream));
     if (rows > 0){
@@ -533,9 +525,21 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
         csr_analyse_kernel<<<grid, 256, 0, ctx->stream>>>(rows, pntr, A->stats_dev);
         HB_LAUNCH_CHECK(ctx);
     }
+    HB_CUDA(cudaMemcpyAsync(&A->max_row_nnz, A->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const bool heavy_tail = (double) A->max_row_nnz > 16.0 * (A->mean_row_nnz + 1.0);
+    // lanes per row from the mean row length.  Heavy-tailed row lengths: a tile whose non-zeros do not fit a ring stage is walked
+    // straight from global memory, so tiles are made of fewer rows (more lanes per row) to keep almost all of them staged
+    // (power-law matrix of configs[4]: see DESIGN.md §4)
+    A->tpr = pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype));
+    {
+        const char *sh = getenv("HB_PIPE_TPR_SHIFT");
+        int shift = !heavy_tail ? 0 : (sh ? atoi(sh) : HB_HEAVY_TPR_SHIFT);
+        while (shift-- > 0 && A->tpr < 16) A->tpr *= 2;
+    }
     // equal-nnz row partition tables for the streaming kernel (one per pipeline configuration)
     const char *cfg_env = getenv("HB_PIPE_CFG");
-    A->pipe_cfg = cfg_env ? ((cfg_env[0] == '1') ? 1 : 0) : (pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype)) >= 4 ? 1 : 0);
+    A->pipe_cfg = cfg_env ? ((cfg_env[0] == '1') ? 1 : 0) : (A->tpr >= 4 ? 1 : 0);
     A->vec_aligned = A->vec_aligned && aligned16p(pntr);
     {   // tile-to-CTA map of the streaming kernel: round-robin sweep by default, contiguous equal-nnz pieces on request
         const char *m = getenv("HB_PIPE_MAP");
@@ -544,9 +548,9 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     if (rows > 0 && nnz > 0 && A->vec_aligned){
         for (int c = 0; c < 2; c++){
             const int threads = c == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
-            const int tile_rows = threads / pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype));
+            const int tile_rows = threads / A->tpr;
             const int ntiles = (rows + tile_rows - 1) / tile_rows;
-            const int occ = pipe_occupancy_any(c, pipe_tpr(A->mean_row_nnz, hb_dtype_size(dtype)), dtype);
+            const int occ = pipe_occupancy_any(c, A->tpr, dtype);
             if (occ < 1) continue;                          // this configuration cannot run here: cta_rows stays null
             int G = ctx->num_sms * occ;
             if (G > ntiles) G = ntiles;
@@ -556,11 +560,10 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
             HB_LAUNCH_CHECK(ctx);
         }
     }
-    HB_CUDA(cudaMemcpyAsync(&A->max_row_nnz, A->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
     // heavy-tailed row lengths: equal-nnz contiguous pieces balance better than the sweep (power-law matrix: 623 vs 674 us);
     // regular matrices: the sweep keeps the gather window of x in L2/L1 (27-point: 117 vs 151 us, 512^3 7-point: -13 % DRAM traffic)
-    if (A->pipe_contiguous < 0) A->pipe_contiguous = ((double) A->max_row_nnz > 16.0 * (A->mean_row_nnz + 1.0)) ? 1 : 0;
+    if (A->pipe_contiguous < 0) A->pipe_contiguous = heavy_tail ? 1 : 0;
     *out = A;
     return HB_OK;
 }
