@@ -84,6 +84,47 @@ template<typename T> void solvers_on_engines(){
     hassert(testvec(ygpu, ycpu, 1.E+6 * hala::norm2(ycpu)));
 }
 
+
+// Row f3 through the header layer: a gpu_sparse_matrix kept across products, op 'T' / 'C' on the cached transpose in its three modes,
+// values rewritten in place between products (the view is non-owning, reference gpu/hala_cuda_sparse_general.hpp:186-190), against
+// hala::sparse_gemv on the CPU engine.
+template<typename T> struct mkval { static T get(double a, double){ return (T) a; } };
+template<typename R> struct mkval<std::complex<R>> { static std::complex<R> get(double a, double b){ return std::complex<R>((R) a, (R) b); } };
+template<typename T> void transposed_products(){
+    current_test<T> tests("gpu sparse T/C cached");
+    using P = hala::get_precision_type<std::vector<T>>;
+    const int n = 9, N = n * n * n;
+    std::vector<int> pntr(1, 0), indx;
+    std::vector<T> vals;
+    for(int k=0; k<n; k++) for(int j=0; j<n; j++) for(int i=0; i<n; i++){        // nonsymmetric 7-point stencil
+        auto add = [&](int kk, int jj, int ii, double v){ if (kk>=0 && kk<n && jj>=0 && jj<n && ii>=0 && ii<n){ indx.push_back((kk*n+jj)*n+ii); vals.push_back(mkval<T>::get(v, 0.125 * v + 0.01 * ii)); } };
+        add(k-1,j,i,-1.5); add(k,j-1,i,-1.25); add(k,j,i-1,-1.125); add(k,j,i,6.0 + 0.01 * i); add(k,j,i+1,-0.875); add(k,j+1,i,-0.75); add(k+1,j,i,-0.5);
+        pntr.push_back((int) indx.size());
+    }
+    std::vector<T> x(N);
+    for(int i=0; i<N; i++) x[i] = mkval<T>::get(std::sin(0.37 * i) + 0.25, std::cos(0.11 * i));
+    hala::gpu_engine egpu(0);
+    auto gp = egpu.load(pntr); auto gi = egpu.load(indx); auto gv = egpu.load(vals); auto gx = egpu.load(x);
+    auto matrix = hala::make_sparse_matrix(egpu, N, gp, gi, gv);
+    P const tol = (std::is_same<P, float>::value) ? (P) 2.E-4 : (P) 1.E-11;
+    auto check = [&](char trans){
+        std::vector<T> yref, y;
+        hala::sparse_gemv(trans, N, N, 2.0, pntr, indx, vals, x, 0.0, yref);
+        hala::gpu_vector<T> gy(egpu.device());
+        matrix.gemv(trans, 2.0, gx, 0.0, gy);
+        gy.unload(y);
+        hassert(testvec(y, yref, tol));
+    };
+    for(int mode : {HB_TRANS_CHECKED, HB_TRANS_FROZEN, HB_TRANS_SCATTER, HB_TRANS_CHECKED}){
+        matrix.set_transpose_mode(mode);
+        check('T'); check('C'); check('N');
+        for(auto &v : vals) v *= hala::get_cast<T>(1.03125);                      // the caller rewrites the values in place
+        gv.load(vals);
+        if (mode == HB_TRANS_FROZEN) matrix.values_changed();
+        check('C'); check('T');
+    }
+}
+
 int main(int argc, char**){
     verbose = (argc > 1);
     std::string name = "REFERENCE TESTS ON THE B200 BACKEND";
@@ -98,6 +139,7 @@ int main(int argc, char**){
         []()->void{ scal<float>(); scal<double>(); scal<std::complex<float>>(); scal<std::complex<double>>(); },
         []()->void{ gemv<float>(); gemv<double>(); gemv<std::complex<float>>(); gemv<std::complex<double>>(); },
         []()->void{ sparse_matvec<float>(); sparse_matvec<double>(); sparse_matvec<std::complex<float>>(); sparse_matvec<std::complex<double>>(); },
+        []()->void{ transposed_products<float>(); transposed_products<double>(); transposed_products<std::complex<float>>(); transposed_products<std::complex<double>>(); },
     };
     for(auto const &t : direct) perform(t);
 
