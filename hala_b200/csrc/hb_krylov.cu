@@ -334,16 +334,25 @@ __global__ void __launch_bounds__(KR_THREADS, 2) multi_axpy_nrm2_kernel(long lon
 }
 
 // w_out = r / sqrt(real(*nrm2sq_dev))   (normalise + append to the basis in one pass; also rewrites r when r_out != null)
-template<typename T>
+template<typename T, bool VEC>
 __global__ void __launch_bounds__(KR_THREADS) scale_copy_kernel(long long rows, const T * __restrict__ r, const T *nrm2sq_dev, T *w_out, T *r_out){
     const real_t<T> inv = real_t<T>(1) / (real_t<T>) sqrt((double) hreal(*nrm2sq_dev));
     const T s = from_real<T>(inv);
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < (size_t) rows; i += stride){
-        T v = hmul(s, r[i]);
-        w_out[i] = v;
-        if (r_out) r_out[i] = v;
-    }
+    constexpr int NV = vec16<T>::N;
+    vec16<T> pk[4];
+    stream_sweep<T, VEC, 4>((size_t) rows,
+        [&](int u, size_t p){ pk[u] = reinterpret_cast<const vec16<T>*>(r)[p]; },
+        [&](int u, size_t p){
+            #pragma unroll
+            for (int k = 0; k < NV; k++) pk[u].v[k] = hmul(s, pk[u].v[k]);
+            reinterpret_cast<vec16<T>*>(w_out)[p] = pk[u];
+            if (r_out) reinterpret_cast<vec16<T>*>(r_out)[p] = pk[u];
+        },
+        [&](size_t i){
+            const T v = hmul(s, r[i]);
+            w_out[i] = v;
+            if (r_out) r_out[i] = v;
+        });
 }
 
 // ------------------------------------------------------------------------------------------------ general gemv (column-major)
@@ -478,8 +487,12 @@ int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const 
 }
 
 int hb_scale_copy_internal(hb_ctx *ctx, int dtype, long long rows, const void *r, const void *nrm2sq_dev, void *w_out, void *r_out){
-    int grid = kr_grid(ctx, rows, KR_THREADS * 4);
-    HB_DISPATCH(dtype, (scale_copy_kernel<T><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, (const T*) r, (const T*) nrm2sq_dev, (T*) w_out, (T*) r_out)));
+    int grid = kr_grid(ctx, rows, KR_THREADS * 8);
+    const bool vec = aligned16(r) && aligned16(w_out) && (!r_out || aligned16(r_out));
+    HB_DISPATCH(dtype, {
+        if (vec) scale_copy_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, (const T*) r, (const T*) nrm2sq_dev, (T*) w_out, (T*) r_out);
+        else     scale_copy_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(rows, (const T*) r, (const T*) nrm2sq_dev, (T*) w_out, (T*) r_out);
+    });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
