@@ -39,6 +39,7 @@ static constexpr int    HB_NUM_TICKETS   = 64;
 static constexpr size_t HB_SCALAR_BYTES  = 4096;
 static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids never exceed this
 
+struct hb_band;                         // per-tile column runs of banded matrices (hb_spmm_band.cu, experimental)
 struct hb_tcache;                       // cached transposed copy behind op 'T' / 'C' (hb_transpose.cu)
 struct hb_csr {
     hb_ctx *ctx = nullptr;
@@ -58,7 +59,9 @@ struct hb_csr {
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
     int  tpr = 1;                       // lanes per row of the streaming kernel: from the mean row length, one notch up for heavy-tailed rows
     hb_tcache *tc = nullptr;            // transpose mode + (lazily built) CSR of A^T; owned
+    hb_band **band_slot = nullptr;      // one owned slot, filled lazily by hb_spmm_band_ok
 };
+void hb_band_delete(hb_band *b);
 hb_tcache* hb_tcache_new();
 void hb_tcache_delete(hb_tcache *tc);
 // op 'N' matrix standing for op(A), op = 'T' / 'C', with up-to-date values; *out = nullptr: use the scatter kernel

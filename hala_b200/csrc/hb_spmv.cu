@@ -516,6 +516,8 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     A->pntr = pntr; A->indx = indx; A->vals = vals;
     A->vec_aligned = aligned16p(indx) && aligned16p(vals);
     A->tc = hb_tcache_new();
+    A->band_slot = new hb_band*[1];
+    A->band_slot[0] = nullptr;
     A->mean_row_nnz = rows > 0 ? (double) nnz / rows : 0.0;
     // one-time analysis: longest row (one tiny kernel, one 4-byte read-back) — decides the tile shape and the tile-to-CTA map below
     A->stats_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048);
@@ -572,6 +574,7 @@ int hb_csr_destroy(hb_csr *csr){
     if (!csr) return HB_OK;
     for (int c = 0; c < 2; c++) if (csr->cta_rows[c]) cudaFree(csr->cta_rows[c]);
     hb_tcache_delete(csr->tc);
+    if (csr->band_slot){ hb_band_delete(csr->band_slot[0]); delete[] csr->band_slot; }
     delete csr;
     return HB_OK;
 }
