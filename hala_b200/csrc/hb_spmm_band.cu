@@ -111,60 +111,85 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity
     }
 }
 
-// Ct[row * NBP + kb] = sum_j a_(row, j) Bt[col_j * NBP + kb]; Bt / Ct interleaved blocks of BD_NBP right-hand sides
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar){
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Ct[row * NBP + kb] = sum_j a_(row, j) Bt[col_j * NBP + kb]; Bt / Ct interleaved blocks of BD_NBP right-hand sides.
+// BD_THREADS consumer threads (TPR lanes per row) + one producer warp.  Per ring stage a `full` barrier (the producer's arrive + the
+// bytes of its bulk copies) and an `empty` barrier (one arrive per consumer warp): no block-wide barrier in the loop, so a consumer
+// warp that is done with a tile moves on to the next one while the others finish, and the producer refills a stage as soon as its
+// last reader has left it.  The producer warp reads the tile descriptors itself (32 + 8 ints, one or two per lane, handed to lane 0
+// by shuffles), one tile ahead of the copies it issues.
 template<typename T, int TPR>
-__global__ void __launch_bounds__(BD_THREADS, 2) spmm_band_kernel(int rows, int nnz, const int * __restrict__ pntr, const T * __restrict__ vals,
-                                                                  const unsigned short * __restrict__ soff, const int * __restrict__ desc, int ntiles,
-                                                                  const T * __restrict__ Bt, T *Ct, int *err){
+__global__ void __launch_bounds__(BD_THREADS + 32, 2) spmm_band_kernel(int rows, int nnz, const int * __restrict__ pntr, const T * __restrict__ vals,
+                                                                       const unsigned short * __restrict__ soff, const int * __restrict__ desc, int ntiles,
+                                                                       const T * __restrict__ Bt, T *Ct, int *err){
     constexpr int ROWS = BD_THREADS / TPR, CAP = bd_cap<T>(), NV = vec16<T>::N, NPK = BD_NBP / NV, MU = (sizeof(T) == 16 ? 2 : 4);
     constexpr size_t VAL_BYTES = (size_t) CAP * sizeof(T), OFF_BYTES = (size_t) CAP * 2, SEG_BYTES = (size_t) BD_SEGROWS * BD_NBP * sizeof(T);
     constexpr size_t STAGE_BYTES = VAL_BYTES + OFF_BYTES + SEG_BYTES;
     static_assert(VAL_BYTES % 16 == 0 && OFF_BYTES % 16 == 0 && SEG_BYTES % 16 == 0, "stage parts must stay 16-byte aligned");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full[BD_STAGES];
+    __shared__ uint64_t full[BD_STAGES], empty[BD_STAGES];
     __shared__ int      stage_a0[BD_STAGES];
-    __shared__ int      dsm[3][BD_DESC];                       // descriptors of the tiles about to be issued (see the loop)
-    const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
+    const int tid = threadIdx.x;
     const int my_ntile = (int) blockIdx.x < ntiles ? (ntiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
     if (my_ntile == 0) return;
     auto stage_vals = [&](int s){ return reinterpret_cast<T*>(smem_raw + (size_t) s * STAGE_BYTES); };
     auto stage_off  = [&](int s){ return reinterpret_cast<unsigned short*>(smem_raw + (size_t) s * STAGE_BYTES + VAL_BYTES); };
     auto stage_seg  = [&](int s){ return reinterpret_cast<T*>(smem_raw + (size_t) s * STAGE_BYTES + VAL_BYTES + OFF_BYTES); };
     if (tid == 0){
-        for (int s = 0; s < BD_STAGES; s++) mbar_init(full + s, 1);
+        for (int s = 0; s < BD_STAGES; s++){ mbar_init(full + s, 1); mbar_init(empty + s, BD_THREADS / 32); }
         fence_mbar_init();
     }
     __syncthreads();
-    const int nnz8 = nnz & ~7;
-    auto tile_desc = [&](int k){ return desc + (size_t) ((int) blockIdx.x + k * (int) gridDim.x) * BD_DESC; };
-    // The producer must not wait for global memory: a tile's descriptor is fetched two tiles ahead by the first BD_DESC threads (load at
-    // the top of an iteration, store to shared memory at its end, behind the tile's arithmetic) and read by thread 0 from shared memory.
-    if (tid < BD_DESC){
-        dsm[0][tid] = tile_desc(0)[tid];
-        if (my_ntile > 1) dsm[1][tid] = tile_desc(1)[tid];
-    }
-    __syncthreads();
-    auto issue = [&](int k){                                  // thread 0 only
-        const int s = k % BD_STAGES;
-        const int *d = dsm[k % 3];
-        const int b0 = d[0], b1 = d[1], nr = d[2];
-        T *sv = stage_vals(s); unsigned short *so = stage_off(s); T *sg = stage_seg(s);
-        const int a0 = b0 & ~7, end8 = (b1 + 7) & ~7;
-        const int nb = max(min(end8, nnz8) - a0, 0);
-        for (int e = a0 + nb; e < min(end8, nnz); e++){ sv[e - a0] = vals[e]; so[e - a0] = soff[e]; }   // ragged end of the arrays by hand
-        uint32_t bytes = (uint32_t) (nb * (sizeof(T) + 2));
-        for (int q = 0; q < nr; q++) bytes += (uint32_t) ((d[21 + q] - d[20 + q]) * BD_NBP * sizeof(T));
-        stage_a0[s] = a0;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(full + s, bytes);
-        if (nb > 0){
-            bulk_g2s(sv, vals + a0, (uint32_t) (nb * sizeof(T)), full + s);
-            bulk_g2s(so, soff + a0, (uint32_t) (nb * 2), full + s);
+
+    if (tid >= BD_THREADS){
+        // ---------------------------------------------------------------- producer warp
+        const int lane = tid - BD_THREADS;
+        const int nnz8 = nnz & ~7;
+        auto tile_desc = [&](int k){ return desc + (size_t) ((int) blockIdx.x + k * (int) gridDim.x) * BD_DESC; };
+        int d0 = __ldg(tile_desc(0) + lane), d1 = (lane < BD_DESC - 32) ? __ldg(tile_desc(0) + 32 + lane) : 0;
+        for (int k = 0; k < my_ntile; k++){
+            const int s = k % BD_STAGES;
+            // this tile's descriptor out of the lanes' registers; the next one is requested before anything is waited for
+            const int c0 = d0, c1 = d1;
+            if (k + 1 < my_ntile){ d0 = __ldg(tile_desc(k + 1) + lane); d1 = (lane < BD_DESC - 32) ? __ldg(tile_desc(k + 1) + 32 + lane) : 0; }
+            auto dget = [&](int i){ const int lo = __shfl_sync(0xffffffffu, c0, i & 31), hi = __shfl_sync(0xffffffffu, c1, i & 31); return i < 32 ? lo : hi; };
+            const int b0 = dget(0), b1 = dget(1), nr = dget(2);
+            if (k >= BD_STAGES){
+                if (!mbar_wait_bounded(empty + s, (uint32_t) (((k / BD_STAGES) - 1) & 1))){ if (lane == 0) atomicExch(err, 1); return; }
+            }
+            T *sv = stage_vals(s); unsigned short *so = stage_off(s); T *sg = stage_seg(s);
+            const int a0 = b0 & ~7, end8 = (b1 + 7) & ~7;
+            const int nb = max(min(end8, nnz8) - a0, 0);
+            uint32_t bytes = (uint32_t) (nb * (sizeof(T) + 2));
+            int off_prev = dget(20);
+            if (lane == 0){
+                for (int e = a0 + nb; e < min(end8, nnz); e++){ sv[e - a0] = vals[e]; so[e - a0] = soff[e]; }   // ragged end of the arrays by hand
+                stage_a0[s] = a0;
+            }
+            bytes += (uint32_t) ((dget(20 + nr) - off_prev) * BD_NBP * sizeof(T));
+            if (lane == 0){
+                fence_proxy_async();
+                mbar_arrive_expect_tx(full + s, bytes);
+                if (nb > 0){
+                    bulk_g2s(sv, vals + a0, (uint32_t) (nb * sizeof(T)), full + s);
+                    bulk_g2s(so, soff + a0, (uint32_t) (nb * 2), full + s);
+                }
+            }
+            for (int q = 0; q < nr; q++){                       // warp-uniform trip count; only lane 0 issues
+                const int start = dget(4 + q), off_next = dget(21 + q);
+                if (lane == 0)
+                    bulk_g2s(sg + (size_t) off_prev * BD_NBP, Bt + (size_t) start * BD_NBP, (uint32_t) ((off_next - off_prev) * BD_NBP * sizeof(T)), full + s);
+                off_prev = off_next;
+            }
         }
-        for (int q = 0; q < nr; q++)
-            bulk_g2s(sg + (size_t) d[20 + q] * BD_NBP, Bt + (size_t) d[4 + q] * BD_NBP, (uint32_t) ((d[21 + q] - d[20 + q]) * BD_NBP * sizeof(T)), full + s);
-    };
-    if (tid == 0) for (int k = 0; k < BD_STAGES - 1 && k < my_ntile; k++) issue(k);
+        return;
+    }
+
+    // -------------------------------------------------------------------- consumers
+    const int sub = tid % TPR, grp = tid / TPR;
     // row bounds are read one tile ahead so that their latency is off the per-tile critical path
     int rs = 0, re = 0;
     {
@@ -173,10 +198,6 @@ __global__ void __launch_bounds__(BD_THREADS, 2) spmm_band_kernel(int rows, int 
     }
     for (int k = 0; k < my_ntile; k++){
         const int s = k % BD_STAGES;
-        int dreg = 0;
-        const bool dfetch = tid < BD_DESC && k + 2 < my_ntile;
-        if (dfetch) dreg = __ldg(tile_desc(k + 2) + tid);
-        if (tid == 0 && k + BD_STAGES - 1 < my_ntile) issue(k + BD_STAGES - 1);
         int nrs = 0, nre = 0;
         if (k + 1 < my_ntile){
             const long long row = ((long long) blockIdx.x + (long long) (k + 1) * gridDim.x) * ROWS + grp;
@@ -212,6 +233,9 @@ __global__ void __launch_bounds__(BD_THREADS, 2) spmm_band_kernel(int rows, int 
                 }
             }
         }
+        // every lane of the warp has read what it needs from the stage: hand it back to the producer
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + s);
         #pragma unroll
         for (int e = 0; e < BD_NBP; e++){
             #pragma unroll
@@ -228,8 +252,6 @@ __global__ void __launch_bounds__(BD_THREADS, 2) spmm_band_kernel(int rows, int 
             }
         }
         rs = nrs; re = nre;
-        if (dfetch) dsm[(k + 2) % 3][tid] = dreg;
-        __syncthreads();                                      // stage s may be refilled
     }
 }
 
@@ -287,13 +309,13 @@ static int launch_band(hb_ctx *ctx, const hb_csr *A, const hb_band *b, const T *
         HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int n = 0;
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, BD_THREADS, smem));
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, BD_THREADS + 32, smem));
         occ = n < 1 ? 1 : n;
     }
     int *err = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048 + 64);
     HB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
     const int grid = std::min(b->ntiles, ctx->num_sms * occ);
-    k<<<grid, BD_THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, (const T*) A->vals, b->soff, b->desc, b->ntiles, Bt, Ct, err);
+    k<<<grid, BD_THREADS + 32, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, (const T*) A->vals, b->soff, b->desc, b->ntiles, Bt, Ct, err);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
