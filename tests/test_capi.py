@@ -58,6 +58,31 @@ def test_argument_errors_are_reported():
     assert capi.lib.hb_ctx_set_pointer_mode(None, 0) == 2
 
 
+def test_enumerations_agree_with_the_header():
+    """The ctypes mirror restates the header's enumerations by value: keep them equal."""
+    from hala_b200 import capi
+    text = open(os.path.join(ROOT, "include", "halab200.h")).read()
+    enums = {}
+    for body in re.findall(r"enum\s*\{([^}]*)\}", text):
+        for name, val in re.findall(r"(HB_[A-Z0-9_]+)\s*=\s*(-?\d+)", body):
+            enums[name] = int(val)
+    assert len(enums) >= 15
+    for name, val in enums.items():
+        if hasattr(capi, name):
+            assert getattr(capi, name) == val, name
+    for name in ("HB_F32", "HB_F64", "HB_C32", "HB_C64", "HB_H2D", "HB_D2H", "HB_D2D", "HB_TRANS_SCATTER", "HB_TRANS_CHECKED", "HB_TRANS_FROZEN"):
+        assert name in enums and hasattr(capi, name), name
+
+
+def test_transpose_entry_points_reject_null_handles():
+    """hb_csr_set_transpose_mode / hb_csr_values_changed / hb_csr_transpose_info validate their handle before touching the device."""
+    from hala_b200 import capi
+    assert capi.lib.hb_csr_set_transpose_mode(None, capi.HB_TRANS_FROZEN) == 2
+    assert capi.lib.hb_csr_values_changed(None) == 2
+    assert capi.lib.hb_csr_transpose_info(None, None, None, None) == 2
+    assert b"invalid argument" in capi.lib.hb_last_error()
+
+
 def test_product_does_not_touch_the_oracle():
     """The oracle is test infrastructure: nothing under hala_b200/ may import, link or mention it."""
     bad = []
