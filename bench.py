@@ -315,8 +315,23 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
-    else:
+        return
+    try:
         run_ours(args)
+    except BaseException as ex:      # a failing rank must say why on stdout before torchrun tears the others down
+        import traceback
+        diag = {"bench_error": repr(ex), "rank": int(os.environ.get("RANK", "0")), "world": int(os.environ.get("WORLD_SIZE", "1")),
+                "traceback": traceback.format_exc().splitlines()[-6:]}
+        try:
+            from hala_b200.capi import lib
+            diag["hb_last_error"] = lib.hb_last_error().decode()
+        except Exception as ex2:
+            diag["hb_last_error"] = f"unavailable: {ex2!r}"
+        diag.update(getattr(ex, "hb_diag", {}))
+        print(json.dumps(diag), flush=True)
+        sys.stderr.write(json.dumps(diag) + "\n")
+        sys.stderr.flush()
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":

@@ -89,7 +89,11 @@ SIGNATURES = {
     "hb_xpby": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "hb_cg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi, C.POINTER(_d)]),
     "hb_gmres": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _pi, C.POINTER(_d)]),
+    "hb_pcg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _pi, C.POINTER(_d)]),
+    "hb_pgmres": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _pi, C.POINTER(_d)]),
 }
+# hb_precon_fn: int (*)(void *user, const void *in_dev, void *out_dev); pass C.cast(PRECON_FN(py_callable), C.c_void_p) (keep the object alive)
+PRECON_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)      # AttributeError here == header/library mismatch

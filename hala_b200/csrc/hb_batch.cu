@@ -14,8 +14,6 @@ static constexpr int BT_THREADS = 256;
 
 bool hb_spmm_interleaved_ok(const hb_csr *A);
 bool hb_spmm_lpc_ok(const hb_csr *A, int nbp);
-bool hb_spmm_band_ok(hb_ctx *ctx, const hb_csr *A);
-int  hb_spmm_band(hb_ctx *ctx, const hb_csr *A, const void *Bt, void *Ct);
 int  hb_spmm_lpc(hb_ctx *ctx, const hb_csr *A, int nbp, int nb, const void *B, size_t sxr, size_t sxc, const void *alpha, const void *beta, void *Cm, size_t ldc);
 int  hb_spmm_interleaved(hb_ctx *ctx, const hb_csr *A, int nbp, const void *Bt, size_t ldbt, void *Ct, size_t ldct);
 
@@ -272,8 +270,6 @@ int hb_spmm(hb_ctx *ctx, const hb_csr *A, char transa, char transb, int b_rows, 
     if (an && A->nnz > 0 && want_il && hb_spmm_interleaved_ok(A) && !(bconj && !bn)){
         const int saved_mode = ctx->pointer_mode;
         int rc = HB_OK;
-        // experimental (HB_SPMM_PATH=band): operand blocks staged in shared memory for banded matrices (hb_spmm_band.cu)
-        const bool band = path_env && path_env[0] == 'b' && hb_spmm_band_ok(ctx, A);
         void *arena = nullptr;
         if ((rc = hb_ctx_workspace(ctx, es * 8 * ((size_t) K + (size_t) M) + 512, &arena)) != HB_OK) return rc;
         char *Bt = (char*) arena, *Ct = Bt + ((es * 8 * (size_t) K + 255) / 256) * 256;
@@ -289,7 +285,7 @@ int hb_spmm(hb_ctx *ctx, const hb_csr *A, char transa, char transb, int b_rows, 
                 if (nbp == 4) interleave_kernel<T, 4><<<gk, 256, 0, ctx->stream>>>(K, nb, Bblk, sb_row, sb_col, (T*) Bt);
                 else          interleave_kernel<T, 8><<<gk, 256, 0, ctx->stream>>>(K, nb, Bblk, sb_row, sb_col, (T*) Bt);
                 ctx->launches++;
-                rc = band ? hb_spmm_band(ctx, A, Bt, Ct) : hb_spmm_interleaved(ctx, A, nbp, Bt, (size_t) nbp, Ct, (size_t) nbp);
+                rc = hb_spmm_interleaved(ctx, A, nbp, Bt, (size_t) nbp, Ct, (size_t) nbp);
                 if (rc == HB_OK){
                     scalar_arg<T> a = make_scalar<T>(ctx, alpha), b = make_scalar<T>(ctx, beta);
                     T *Cblk = (T*) C + (size_t) n0 * (size_t) ldc;

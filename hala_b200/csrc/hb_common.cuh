@@ -31,6 +31,7 @@ struct hb_ctx {
     // the streaming kernel then waits for the halo flags of `peer_epoch` before it gathers and publishes its <x,y> partial
     const void *peer_hook = nullptr;    // peer_view* in device memory
     unsigned long long peer_epoch = 0;
+    int peer_trot = 0, peer_twait = 0;  // tile rotation / first tile that needs the halo (hb_spmv_pipe.cuh), from hb_csr_halo_order
 };
 int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr);
 
@@ -39,7 +40,6 @@ static constexpr int    HB_NUM_TICKETS   = 64;
 static constexpr size_t HB_SCALAR_BYTES  = 4096;
 static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids never exceed this
 
-struct hb_band;                         // per-tile column runs of banded matrices (hb_spmm_band.cu, experimental)
 struct hb_tcache;                       // cached transposed copy behind op 'T' / 'C' (hb_transpose.cu)
 struct hb_csr {
     hb_ctx *ctx = nullptr;
@@ -59,13 +59,16 @@ struct hb_csr {
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
     int  tpr = 1;                       // lanes per row of the streaming kernel: from the mean row length, one notch up for heavy-tailed rows
     hb_tcache *tc = nullptr;            // transpose mode + (lazily built) CSR of A^T; owned
-    hb_band **band_slot = nullptr;      // one owned slot, filled lazily by hb_spmm_band_ok
+    // row-partitioned runs (local matrix = [owned | ghost] columns, ghosts = columns >= rows): rotation of the streaming kernel's
+    // tile sweep that puts the tiles touching ghost columns last, and the first position of the rotated order that touches one
+    // (hb_csr_halo_order, computed once on first use)
+    mutable int halo_state = 0, halo_trot = 0, halo_twait = 0;
 };
-void hb_band_delete(hb_band *b);
 hb_tcache* hb_tcache_new();
 void hb_tcache_delete(hb_tcache *tc);
 // op 'N' matrix standing for op(A), op = 'T' / 'C', with up-to-date values; *out = nullptr: use the scatter kernel
 int hb_csr_transposed(hb_ctx *ctx, const hb_csr *A, char trans, const hb_csr **out);
+int hb_csr_halo_order(hb_ctx *ctx, const hb_csr *A, int *trot, int *twait);
 
 void hb_set_error(const std::string &msg);
 int  hb_cuda_fail(cudaError_t e, const char *what);
@@ -262,6 +265,20 @@ __device__ __forceinline__ void stream_sweep(size_t n, FL load, FF finish, FS sc
     }
     for (size_t j = done + gtid; j < n; j += stride) scalar(j);
 }
+
+// Function attributes (dynamic shared memory opt-in, carve-out) and occupancy belong to ONE device: the reference's test mains
+// create a gpu_engine for every device of the box in one process (tests/sparse_tests.cpp:52), so "already configured" is kept
+// per device.  Set twice by two host threads at once is harmless.
+struct per_device_flag {
+    unsigned long long mask[4] = {0, 0, 0, 0};          // 256 devices
+    bool first_time(int dev){
+        const unsigned d = (unsigned) dev & 255u;
+        if (mask[d >> 6] >> (d & 63) & 1ull) return false;
+        mask[d >> 6] |= 1ull << (d & 63);
+        return true;
+    }
+};
+
 
 // dtype dispatch on the host
 #define HB_DISPATCH(dtype, ...) \

@@ -68,9 +68,15 @@ struct hb_dist {
     size_t pbuf_ext_bytes = 0;          // bytes of one p buffer
     void  *peer_base[HB_MAX_PEERS] = {};// rank q's exchange buffer as mapped into this process (q == rank: pbuf)
     peer_view *pv_dev = nullptr;
-    unsigned long long epoch = 0;       // global iteration number of the peer protocol; same on every rank
-    unsigned long long vepoch = 0;      // number of peer vector all-reduces so far; same on every rank
+    // Sequence numbers of the peer protocol.  They MUST be equal on all ranks, and nothing a single host observes on its own
+    // (how many batches it happened to enqueue before it saw the done flag) may enter them: every solve re-bases them with one
+    // all-reduce(MAX) (peer_epoch_agree) and advances them by counts all ranks agree on.
+    unsigned long long epoch = 0;       // global iteration number: halo flags and scalar slots carry epoch + 1
+    unsigned long long vepoch = 0;      // number of peer vector all-reduces so far
     int    plan_version = 0;
+    bool   peer_disabled = false;       // a wait timed out once: this communicator stays on NCCL, whatever plan comes next
+    int    peer_fallbacks = 0;          // solves that gave up on the peer transport (time-out) and were redone over NCCL
+    int    epoch_repairs = 0;           // peer_epoch_agree calls that found the ranks' counters different
 };
 
 hb_ctx* hb_dist_context(hb_dist *d){ return d->ctx; }
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(DK_THREADS, 4) pcg_direction_kernel(int n, cg_
                 x4[i] = vx[u]; pn4[i] = vp[u];
             },
             [&](size_t j){ const T pj = p_old[j]; x[j] = hfma(a, pj, x[j]); p_new[j] = hfma(beta, pj, r[j]); });
-    }else{
+    }else if (nrm == nrm){                      // a NaN residual (peer time-out, breakdown) leaves x at the last good iterate
         stream_sweep<T, VEC, U>((size_t) n,
             [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = po4[i]; },
             [&](int u, size_t i){
@@ -404,6 +410,11 @@ int peer_setup(hb_dist *d, size_t es){
     peer_view pv;
     memset(&pv, 0, sizeof(pv));
     pv.rank = d->rank; pv.world = W; pv.nneigh = (int) d->neigh.size();
+    {   // ~4 s of GPU clock by default; HB_PEER_TIMEOUT_MS shortens it (tests of the time-out / fallback path)
+        const char *e = getenv("HB_PEER_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 4000.0;
+        pv.timeout_clocks = (long long) ((ms > 1.0 ? ms : 1.0) * 2.0e6);
+    }
     for (int q = 0; q < W; q++) pv.mail[q] = reinterpret_cast<peer_mailbox*>(d->peer_base[q]);
     int soff = 0;
     for (int k = 0; k < pv.nneigh; k++){
@@ -428,19 +439,55 @@ int peer_setup(hb_dist *d, size_t es){
     return HB_OK;
 }
 
-// CG over the peer transport; see the kernel block above for the per-iteration protocol
-int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+// All ranks leave with the same epoch / vepoch: the maximum over ranks (a rank whose counters ran ahead published nothing beyond
+// what the others expect: flags only ever carry values <= the publishing rank's own counter).  One 16-byte all-reduce and one host
+// synchronisation per solve; it also fences this solve's peer traffic from the previous one's.
+int peer_epoch_agree(hb_dist *d){
+    hb_ctx *ctx = d->ctx;
+    unsigned long long *dv = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->dscalars) + 3072);
+    unsigned long long *hv = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->hscalars) + 640);
+    static const bool off = [](){ const char *e = getenv("HB_DEBUG_NO_EPOCH_AGREE"); return e && e[0] == '1'; }();
+    if (off) return HB_OK;                          // test hook: reproduces the round-1 behaviour (per-host counting only)
+    const unsigned long long mine[2] = {d->epoch, d->vepoch};
+    hv[0] = mine[0]; hv[1] = mine[1];
+    HB_CUDA(cudaMemcpyAsync(dv, hv, 16, cudaMemcpyHostToDevice, ctx->stream));
+    HB_NCCL(g_nccl.AllReduce(dv, dv, 2, ncclUint64, ncclMax, d->comm, ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(hv, dv, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hv[0] != mine[0] || hv[1] != mine[1]) d->epoch_repairs++;
+    d->epoch = hv[0]; d->vepoch = hv[1];
+    return HB_OK;
+}
+// maximum over ranks of the local mailbox's error flag (0 / 1), cleared on the way; enqueued behind the solve, one host sync
+int peer_error_agree(hb_dist *d, int *any){
+    hb_ctx *ctx = d->ctx;
+    peer_mailbox *mail = reinterpret_cast<peer_mailbox*>(d->pbuf);
+    int *dv = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 3072 + 64);
+    int *hv = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->hscalars) + 640 + 64);
+    HB_CUDA(cudaMemcpyAsync(dv, &mail->error, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    HB_CUDA(cudaMemsetAsync(&mail->error, 0, sizeof(int), ctx->stream));
+    HB_NCCL(g_nccl.AllReduce(dv, dv, 1, ncclInt32, ncclMax, d->comm, ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(hv, dv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *any = *hv;
+    return HB_OK;
+}
+
+// CG over the peer transport; see the kernel block above for the per-iteration protocol.
+// *timed_out = 1 (on ALL ranks, agreed): a wait on a peer's flag gave up somewhere; x holds the last good iterate, *iters the
+// operator applications spent so far, and the caller redoes the solve over NCCL.
+int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res, int *timed_out){
     hb_ctx *ctx = d->ctx;
     const int n = d->n_owned, dtype = A->dtype;
     const size_t es = hb_dtype_size(dtype);
     const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256;
     void *arena = nullptr;
     int rc;
+    *timed_out = 0;
     if ((rc = hb_ctx_workspace(ctx, 2 * vec_bytes + 256, &arena)) != HB_OK) return rc;       // r | Ap | state
     char *base = (char*) arena;
     void *r = base, *Ap = base + vec_bytes, *state = base + 2 * vec_bytes;
     char *pb[2] = {(char*) d->pbuf + HB_MAILBOX_BYTES, (char*) d->pbuf + HB_MAILBOX_BYTES + d->pbuf_ext_bytes};
-    peer_mailbox *mail = reinterpret_cast<peer_mailbox*>(d->pbuf);
     cg_dhost *hstat = reinterpret_cast<cg_dhost*>(reinterpret_cast<char*>(ctx->hscalars) + 512);
     void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 512;
     hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
@@ -448,10 +495,20 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
     if (grid < PK_MIN_GRID) grid = PK_MIN_GRID;
     const bool fused = peer_env_fused_spmv() && hb_spmv_variant(A) == 3;
     const peer_view *pv = d->pv_dev;
+    int trot = 0, twait = 0;
+    if (fused && (rc = hb_csr_halo_order(ctx, A, &trot, &twait)) != HB_OK) return rc;
+    {   // HB_PEER_HALO_DEFER=0: wait for the halo before the first gather of every CTA, natural tile order (A/B probe)
+        const char *e = getenv("HB_PEER_HALO_DEFER");
+        if (e && e[0] == '0'){ trot = 0; twait = 0; }
+    }
+
+    // the ranks' sequence numbers are re-based first (see hb_dist::epoch); g0 = the number of this solve's first iteration
+    if ((rc = peer_epoch_agree(d)) != HB_OK) return rc;
+    const unsigned long long g0 = d->epoch;
 
     // p0 <- x0 (owned) + halo over NCCL; Ap = A x0; r = b - Ap; p0 = r; <r,r> all-reduced over NCCL (this also fences the
     // previous solve's peer traffic from this one's); then the first halo push
-    void *p0 = pb[d->epoch & 1];
+    void *p0 = pb[g0 & 1];
     HB_CUDA(cudaMemcpyAsync(p0, x, es * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = hb_dist_halo_exchange_nccl(d, dtype, p0)) != HB_OK) return rc;
     if ((rc = hb_spmv_internal(ctx, A, p0, Ap, nullptr)) != HB_OK) return rc;
@@ -461,7 +518,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
                                                                                            ctx->partials, ctx->tickets + 6);
         HB_LAUNCH_CHECK(ctx);
         if ((rc = hb_dist_allreduce_sum_nccl(d, dtype, &st->rr, 1)) != HB_OK) return rc;
-        pcg_begin_kernel<T><<<HB_HALO_BLOCKS, DK_THREADS, 0, ctx->stream>>>(st, pv, d->epoch, d->send_idx, (const T*) p0);
+        pcg_begin_kernel<T><<<HB_HALO_BLOCKS, DK_THREADS, 0, ctx->stream>>>(st, pv, g0, d->send_idx, (const T*) p0);
         HB_LAUNCH_CHECK(ctx);
     });
 
@@ -471,17 +528,20 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
     const int batch = 8;
     long long it = 0;
     int status = HB_OK;
+    // How many batches get enqueued before this host sees the done flag depends on host timing and differs between ranks.  That is
+    // harmless for the protocol — iterations past the stop are skipped by the done flag and publish nothing — as long as the count
+    // never reaches d->epoch: g is derived from g0 and the iteration index only.
     for (long long bidx = 0; status == HB_OK; bidx++){
         for (int j = 0; j < batch && status == HB_OK; j++, it++){
             const int parity = (int) (it & 1);
-            const unsigned long long g = d->epoch++;
+            const unsigned long long g = g0 + (unsigned long long) it;
             void *p_old = pb[g & 1], *p_new = pb[(g + 1) & 1];
             const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
             HB_DISPATCH(dtype, {
                 cg_dstate<T> *st = (cg_dstate<T>*) state;
                 const bool vec = aligned16(x) && aligned16(r) && aligned16(Ap) && aligned16(p_old) && aligned16(p_new);
                 if (fused){
-                    ctx->peer_hook = pv; ctx->peer_epoch = g;
+                    ctx->peer_hook = pv; ctx->peer_epoch = g; ctx->peer_trot = trot; ctx->peer_twait = twait;
                     status = hb_spmv_dot_internal(ctx, A, p_old, Ap, &st->pAp_local, &st->done[parity]);
                     ctx->peer_hook = nullptr;
                     if (status != HB_OK) break;
@@ -510,19 +570,29 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
             if (hstat->done) break;
         }
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-    if (status != HB_OK) return status;
-    if (e != cudaSuccess) return hb_cuda_fail(e, "cudaStreamSynchronize");
-    int perr = 0;
-    HB_CUDA(cudaMemcpy(&perr, &mail->error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (perr){
-        HB_CUDA(cudaMemset(&mail->error, 0, sizeof(int)));
-        hb_set_error("peer transport: a wait on a peer's flag timed out");
-        return HB_ERR_NCCL;
+    {   // test hook: odd ranks count extra batches, as a host that saw the done flag late would have enqueued (and the done flag
+        // skipped) them
+        static const int skew = [](){ const char *e = getenv("HB_DEBUG_EPOCH_SKEW"); return e ? atoi(e) : 0; }();
+        if (skew > 0 && (d->rank & 1)) it += (long long) batch * skew;
     }
+    // the done flag stopped every rank at the same iteration: the (identical) number of operator applications is what the
+    // sequence number advances by.  A solve that failed leaves the per-host count; the next peer_epoch_agree repairs it.
+    int any_timeout = 0;
+    if (status == HB_OK) status = peer_error_agree(d, &any_timeout);        // synchronises the stream
+    else cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    // HB_DEBUG_EPOCH_RULE=host: the round-1 rule (every host counts what it enqueued), kept as a test hook
+    static const bool host_rule = [](){ const char *e = getenv("HB_DEBUG_EPOCH_RULE"); return e && e[0] == 'h'; }();
+    if (status != HB_OK || any_timeout || host_rule) d->epoch = g0 + (unsigned long long) it;
+    else d->epoch = g0 + (unsigned long long) hstat->iterations + 1;
+    if (status != HB_OK) return status;
     if (iters) *iters = hstat->iterations;
     if (res) *res = hstat->rnorm;
+    if (any_timeout){
+        *timed_out = 1;
+        hb_set_error("peer transport: a wait on a peer's flag timed out (rank " + std::to_string(d->rank) + ", epoch " + std::to_string(g0) + " + " +
+                     std::to_string(hstat->iterations) + ")");
+    }
     return HB_OK;
 }
 }
@@ -568,6 +638,15 @@ int hb_dist_transport(const hb_dist *d, int *transport){
     return HB_OK;
 }
 
+int hb_dist_debug_info(const hb_dist *d, unsigned long long *epoch, unsigned long long *vepoch, int *peer_fallbacks, int *epoch_repairs){
+    HB_ARG(d, "dist is null");
+    if (epoch) *epoch = d->epoch;
+    if (vepoch) *vepoch = d->vepoch;
+    if (peer_fallbacks) *peer_fallbacks = d->peer_fallbacks;
+    if (epoch_repairs) *epoch_repairs = d->epoch_repairs;
+    return HB_OK;
+}
+
 int hb_dist_info(const hb_dist *d, int *rank, int *world){
     HB_ARG(d, "dist is null");
     if (rank) *rank = d->rank;
@@ -587,7 +666,7 @@ int hb_dist_set_plan(hb_dist *d, int n_owned, int n_ghost, int nneigh, const int
         if (rc != HB_OK) return rc;
         peer_release(d);
     }
-    d->peer_state = 0; d->plan_version++;
+    d->peer_state = d->peer_disabled ? -1 : 0; d->plan_version++;
     d->n_owned = n_owned; d->n_ghost = n_ghost;
     d->neigh.assign(neigh, neigh + nneigh);
     d->send_count.assign(send_count, send_count + nneigh);
@@ -671,12 +750,32 @@ int hb_dist_allreduce_sum(hb_dist *d, int dtype, void *dev_scalars, int count){
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
-// brings the peer transport up for this element size when it is available (collective); HB_OK either way unless something failed
+// brings the peer transport up for this element size when it is available (collective) and re-bases the ranks' sequence numbers;
+// HB_OK either way unless something failed
 int hb_dist_prepare_transport(hb_dist *d, int dtype){
     HB_ARG(d, "null");
     if (d->world > 1 && d->world <= HB_MAX_PEERS && peer_env_enabled()){
         int prc = peer_setup(d, hb_dtype_size(dtype));
         if (prc != HB_OK && prc != HB_ERR_UNSUPPORTED) return prc;
+        if (prc == HB_OK && (prc = peer_epoch_agree(d)) != HB_OK) return prc;
+    }
+    return HB_OK;
+}
+// collective, after a solve that used the public halo / all-reduce forms: *timed_out = 1 on all ranks when a wait on a peer's flag
+// gave up anywhere; the peer buffers are then given back and the communicator stays on NCCL (the caller redoes its solve)
+int hb_dist_finish_transport(hb_dist *d, int *timed_out){
+    HB_ARG(d && timed_out, "null");
+    *timed_out = 0;
+    if (d->peer_state != 1) return HB_OK;
+    int any = 0, rc = peer_error_agree(d, &any);
+    if (rc != HB_OK) return rc;
+    if (any){
+        hb_set_error("peer transport: a wait on a peer's flag timed out (rank " + std::to_string(d->rank) + ")");
+        if (getenv("HB_DIST_VERBOSE")) fprintf(stderr, "[hb_dist rank %d] %s -> redoing the solve over NCCL\n", d->rank, hb_last_error());
+        d->peer_fallbacks++;
+        peer_release(d);
+        d->peer_state = -1; d->peer_disabled = true;
+        *timed_out = 1;
     }
     return HB_OK;
 }
@@ -699,7 +798,26 @@ int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, 
     // otherwise NCCL send/recv + all-reduce.  The choice is agreed by all ranks inside peer_setup.
     if (d->world > 1 && d->world <= HB_MAX_PEERS && peer_env_enabled()){
         int prc = peer_setup(d, es);
-        if (prc == HB_OK) return dist_cg_peer(d, A, b, x, tol, max_iter, iters, res);
+        if (prc == HB_OK){
+            int timed_out = 0, it_peer = 0;
+            double res_peer = 0;
+            prc = dist_cg_peer(d, A, b, x, tol, max_iter, &it_peer, &res_peer, &timed_out);
+            if (prc != HB_OK) return prc;
+            if (!timed_out){ if (iters) *iters = it_peer; if (res) *res = res_peer; return HB_OK; }
+            // Agreed by all ranks: some wait on a peer's flag gave up.  x is the last good iterate on every rank; the peer buffers
+            // are given back and this communicator stays on NCCL.  The solve restarts from x, so the iteration count is that of a
+            // restarted CG: operator applications of both legs are reported together.
+            if (getenv("HB_DIST_VERBOSE")) fprintf(stderr, "[hb_dist rank %d] %s -> redoing the solve over NCCL\n", d->rank, hb_last_error());
+            d->peer_fallbacks++;
+            peer_release(d);
+            d->peer_state = -1; d->peer_disabled = true;
+            const int spent = it_peer > 1 ? it_peer - 1 : 0;
+            max_iter = max_iter > spent + 2 ? max_iter - spent : 2;
+            int it2 = 0;
+            prc = hb_dist_cg(d, A, b, x, tol, max_iter, &it2, res);
+            if (iters) *iters = spent + it2;
+            return prc;
+        }
         if (prc != HB_ERR_UNSUPPORTED) return prc;
     }
     const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256, ext_bytes = ((es * ((size_t) n + d->n_ghost) + 255) / 256) * 256;

@@ -34,7 +34,7 @@ struct cg_host_status { volatile int done; volatile int iterations; volatile dou
 // r -= a q ; rr = <r, r> ; then (last block) bookkeeping of solve_cg_core: iterations, stop test, zr_next
 template<typename T, bool VEC>
 __global__ void __launch_bounds__(KR_THREADS, 4) cg_update_kernel(int n, cg_state<T> *st, int parity, const T * __restrict__ q, T *r,
-                                                               void *partials_v, unsigned int *ticket, cg_host_status *host){
+                                                               void *partials_v, unsigned int *ticket, cg_host_status *host, int precond){
     __shared__ double red[32];
     if (st->done) return;
     const T na = hneg(hdiv(st->zr[parity], st->pAp));
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(KR_THREADS, 4) cg_update_kernel(int n, cg_stat
     if (last_block_arrives(ticket)){
         double rr = sum_partials<double>(partials, gridDim.x, 1, red);
         if (threadIdx.x == 0){
-            st->zr[parity ^ 1] = from_real<T>((real_t<T>) rr);
+            if (!precond) st->zr[parity ^ 1] = from_real<T>((real_t<T>) rr);    // preconditioned run: <r,z> comes from pcg_dot_kernel
             const double nrm = sqrt(rr);
             st->rnorm = nrm;
             const int it = st->iterations + 1;  // iterations++ of solve_cg_core: one more operator application
@@ -101,6 +101,35 @@ __global__ void __launch_bounds__(KR_THREADS, 4) cg_direction_kernel(int n, cons
                 x4[i] = vx[u];
             },
             [&](size_t j){ x[j] = hfma(a, p[j], x[j]); });
+}
+
+// Preconditioned CG (hb_pcg): zr[slot] = <r, z> (conjugated on r, as hala::dot) once the caller's preconditioner has produced z;
+// with p_out != null (start of the solve) also p = z.  Skipped once the stop flag is up.
+template<typename T, bool VEC>
+__global__ void __launch_bounds__(KR_THREADS, 4) pcg_dot_kernel(int n, cg_state<T> *st, int slot, const T * __restrict__ r, const T * __restrict__ z, T *p_out,
+                                                             void *partials_v, unsigned int *ticket){
+    __shared__ T red[32];
+    if (st->done) return;
+    T acc = zero_of<T>();
+    constexpr int U = 4;
+    vec16<T> vr[U], vz[U];
+    const vec16<T> *r4 = reinterpret_cast<const vec16<T>*>(r), *z4 = reinterpret_cast<const vec16<T>*>(z);
+    vec16<T> *p4 = reinterpret_cast<vec16<T>*>(p_out);
+    stream_sweep<T, VEC, U>((size_t) n,
+        [&](int u, size_t i){ vr[u] = r4[i]; vz[u] = z4[i]; },
+        [&](int u, size_t i){
+            #pragma unroll
+            for (int k = 0; k < vec16<T>::N; k++) acc = hfma(hconj(vr[u].v[k]), vz[u].v[k], acc);
+            if (p_out) p4[i] = vz[u];
+        },
+        [&](size_t j){ const T zj = z[j]; acc = hfma(hconj(r[j]), zj, acc); if (p_out) p_out[j] = zj; });
+    T *partials = reinterpret_cast<T*>(partials_v);
+    T b = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_arrives(ticket)){
+        T total = sum_partials<T>(partials, gridDim.x, 1, red);
+        if (threadIdx.x == 0) st->zr[slot] = total;
+    }
 }
 
 // setup: r = b - q (q = A x0), p = r, zr[0] = <r,r>; state initialised by the last block
@@ -417,11 +446,10 @@ template<typename T, int MODE, bool CONJ>
 static int launch_gs_pipe(hb_ctx *ctx, long long rows, int k, const T *W, size_t ldw, const T *r_in, T *r_out, const T *h_dev, T scale,
                           unsigned int *ticket, T *out, const int *skip){
     auto kern = gs_pipe_kernel<T, MODE, CONJ>;
-    static bool configured = false;
-    if (!configured){
+    static per_device_flag configured;
+    if (configured.first_time(ctx->device)){
         HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gs_smem_bytes<T>()));
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     const long long per16 = 16 / sizeof(T), rows_al = rows - rows % per16;
     const long long ntiles = (rows_al + GS_R - 1) / GS_R;
@@ -505,14 +533,24 @@ int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol,
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
-int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host){
+int hb_pcg_dot_internal(hb_ctx *ctx, int dtype, int n, void *state, int slot, const void *r, const void *z, void *p_out){
+    int grid = kr_grid(ctx, n, KR_THREADS * 8);
+    const bool vec = aligned16(r) && aligned16(z) && aligned16(p_out);
+    HB_DISPATCH(dtype, {
+        if (vec) pcg_dot_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, slot, (const T*) r, (const T*) z, (T*) p_out, ctx->partials, ctx->tickets + 4);
+        else     pcg_dot_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, slot, (const T*) r, (const T*) z, (T*) p_out, ctx->partials, ctx->tickets + 4);
+    });
+    HB_LAUNCH_CHECK(ctx);
+    return HB_OK;
+}
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host, int precond){
     int grid = kr_grid(ctx, n, KR_THREADS * 8);
     const bool vec = aligned16(q) && aligned16(r);
     HB_DISPATCH(dtype, {
         if (vec) cg_update_kernel<T, true><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) q, (T*) r,
-                                                                                  ctx->partials, ctx->tickets + 4, (cg_host_status*) host);
+                                                                                  ctx->partials, ctx->tickets + 4, (cg_host_status*) host, precond);
         else     cg_update_kernel<T, false><<<grid, KR_THREADS, 0, ctx->stream>>>(n, (cg_state<T>*) state, parity, (const T*) q, (T*) r,
-                                                                                   ctx->partials, ctx->tickets + 4, (cg_host_status*) host);
+                                                                                   ctx->partials, ctx->tickets + 4, (cg_host_status*) host, precond);
     });
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;

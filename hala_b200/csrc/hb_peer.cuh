@@ -36,6 +36,7 @@ static_assert(sizeof(peer_mailbox) <= HB_MAILBOX_BYTES, "mailbox layout");
 // what a kernel needs to reach its peers (lives in device memory, built by peer_setup)
 struct peer_view {
     int rank, world, nneigh, pad;
+    long long timeout_clocks;                   // a wait gives up after this many GPU clocks (default ~4 s; HB_PEER_TIMEOUT_MS)
     peer_mailbox *mail[HB_MAX_PEERS];           // mailbox of rank q as mapped here (q == rank: the local one)
     int neigh[HB_MAX_NEIGH];                    // rank of halo neighbour k
     int recv_from[HB_MAX_NEIGH];                // 1 when neighbour k sends us ghost entries
@@ -56,13 +57,14 @@ __device__ __forceinline__ double ld_volatile_f64(const double *p){
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *flag >= target; gives up after ~4 s of GPU clock (a peer that died must not hang this GPU): returns false
-__device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long target){
+// spin until *flag >= target; gives up after pv->timeout_clocks (~4 s of GPU clock by default: a peer that died must not hang
+// this GPU): returns false
+__device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long target, long long timeout_clocks){
     if (ld_acquire_sys(flag) >= target) return true;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < target){
         __nanosleep(40);
-        if (clock64() - t0 > 8000000000LL) return false;
+        if (clock64() - t0 > timeout_clocks) return false;
     }
     return true;
 }
@@ -102,7 +104,7 @@ template<typename T> __device__ __forceinline__ T peer_wait_sum(const peer_view 
     bool ok = true;
     for (int s0 = q; s0 < W; s0 += 32){         // W <= 16: one trip
         const peer_slot *s = &mine->slot[channel][g & 1][s0];
-        ok = peer_spin(&s->seq, g + 1);
+        ok = peer_spin(&s->seq, g + 1, pv->timeout_clocks);
         a = ld_volatile_f64(&s->v[0]); b = ld_volatile_f64(&s->v[1]);
     }
     if (!__all_sync(0xffffffffu, ok)){
@@ -125,7 +127,7 @@ __device__ __forceinline__ bool peer_halo_wait(const peer_view *pv, unsigned lon
     for (int k = 0; k < pv->nneigh; k++){
         if (!pv->recv_from[k]) continue;
         for (int b = lane; b < HB_HALO_BLOCKS; b += 32)
-            ok = peer_spin(&mine->halo_seq[pv->neigh[k]][b], g + 1) && ok;
+            ok = peer_spin(&mine->halo_seq[pv->neigh[k]][b], g + 1, pv->timeout_clocks) && ok;
     }
     ok = __all_sync(0xffffffffu, ok);
     if (!ok && lane == 0) mine->error = 1;
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(128) peer_allsum_kernel(const peer_view *pv, u
     __shared__ int ok_s;
     if (t == 0) ok_s = 1;
     __syncthreads();
-    if (t < W && !peer_spin(&mine->vslot[v & 1][t].seq, v + 1)) ok_s = 0;
+    if (t < W && !peer_spin(&mine->vslot[v & 1][t].seq, v + 1, pv->timeout_clocks)) ok_s = 0;
     __syncthreads();
     if (t < count){
         double sa = 0.0, sb = 0.0;

@@ -10,11 +10,13 @@
 #include <vector>
 #include <cmath>
 #include <cstdlib>
+#include <string>
 
 hb_ctx* hb_dist_context(hb_dist *d);
 int hb_dist_owned(const hb_dist *d);
 int hb_dist_ghosts(const hb_dist *d);
 extern "C" int hb_dist_prepare_transport(hb_dist *d, int dtype);
+extern "C" int hb_dist_finish_transport(hb_dist *d, int *timed_out);
 
 int hb_spmv_dot_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev, const int *skip);
 int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const int *skip);
@@ -23,7 +25,8 @@ int hb_multi_axpy_internal(hb_ctx *ctx, int dtype, long long rows, int k, const 
                            void *nrm2sq_dev, double scale, const int *skip);
 int hb_scale_copy_internal(hb_ctx *ctx, int dtype, long long rows, const void *r, const void *nrm2sq_dev, void *w_out, void *r_out);
 int hb_cg_setup_internal(hb_ctx *ctx, int dtype, int n, void *state, double tol, int max_iter, const void *b, const void *q, void *r, void *p, void *host);
-int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host);
+int hb_cg_update_internal(hb_ctx *ctx, int dtype, int n, void *state, int parity, const void *q, void *r, void *host, int precond);
+int hb_pcg_dot_internal(hb_ctx *ctx, int dtype, int n, void *state, int slot, const void *r, const void *z, void *p_out);
 int hb_cg_direction_internal(hb_ctx *ctx, int dtype, int n, const void *state, int parity, int it_now, const void *r, void *p, void *x);
 size_t hb_cg_state_bytes(int dtype);
 size_t hb_cg_state_pap_offset(int dtype);
@@ -98,8 +101,20 @@ template<typename T> void h_tpsv_unn(int n, const std::vector<T> &ap, std::vecto
     }
 }
 
+// the caller's preconditioner as the solvers see it: out = P^-1 in on the context's stream; a non-zero return aborts the solve
+struct precon_call {
+    hb_precon_fn fn = nullptr;
+    void *user = nullptr;
+    int operator()(const void *in, void *out) const{
+        const int rc = fn(user, in, out);
+        if (rc != 0){ hb_set_error("the preconditioner callback returned " + std::to_string(rc)); return HB_ERR_CALLBACK; }
+        return HB_OK;
+    }
+};
+
 template<typename T>
-int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, double tol_d, int max_outer, int restart, int cproj, int *iters, double *res){
+int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, double tol_d, int max_outer, int restart, int cproj, int *iters, double *res,
+                precon_call precon = precon_call()){
     using R = real_t<T>;
     const int n = A->rows;
     const R tol = (R) tol_d;
@@ -120,10 +135,13 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
         if (vec_bytes >= page && pad_pages > 0 && ((vec_bytes + page - 1) / page) % 2 == 0) vec_bytes += pad_pages * page;
     }
     void *arena = nullptr;
-    if ((rc = hb_ctx_workspace(ctx, vec_bytes * ((size_t) restart + 2) + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
+    // with a preconditioner the operator's output (ta) and the preconditioned vector (t = P^-1 ta) are two arrays; without, one
+    const size_t nvec = (size_t) restart + 2 + (precon.fn ? 1 : 0);
+    if ((rc = hb_ctx_workspace(ctx, vec_bytes * nvec + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
     T *t = (T*) arena, *W = (T*) ((char*) arena + vec_bytes);
     T *xext = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 1));
-    T *hdev = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 2));
+    T *ta = precon.fn ? (T*) ((char*) arena + vec_bytes * ((size_t) restart + 2)) : t;
+    T *hdev = (T*) ((char*) arena + vec_bytes * nvec);
     const size_t ldw = vec_bytes / sizeof(T);
     auto halo = [&](T *v)->int{ return dist ? hb_dist_halo_exchange(dist, A->dtype, v) : HB_OK; };
     auto allsum = [&](T *v, int count)->int{ return dist ? hb_dist_allreduce_sum(dist, A->dtype, v, count) : HB_OK; };
@@ -143,14 +161,15 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
     while ((outer_res > tol) && (outer < max_outer)){
         H.clear(); S.clear(); C.clear(); Z.clear();
         // t = b - A x ; r = P^-1 t (identity) ; inner_res = ||r|| ; W[:,0] = r / ||r||
-        HB_CUDA(cudaMemcpyAsync(t, b, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+        HB_CUDA(cudaMemcpyAsync(ta, b, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
         const T *xin = x;
         if (dist){
             HB_CUDA(cudaMemcpyAsync(xext, x, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
             if ((rc = halo(xext)) != HB_OK) return rc;
             xin = xext;
         }
-        if ((rc = hb_spmv(ctx, A, 'N', &mone, xin, &one, t)) != HB_OK) return rc;
+        if ((rc = hb_spmv(ctx, A, 'N', &mone, xin, &one, ta)) != HB_OK) return rc;
+        if (precon.fn && (rc = precon(ta, t)) != HB_OK) return rc;                                           // r = P^-1 t  (gmres:176)
         total++;
         if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, 0, t, 0, t, t, hdev, -1.0, nullptr)) != HB_OK) return rc;     // hdev[0] = ||t||^2
         if ((rc = allsum(hdev, 1)) != HB_OK) return rc;
@@ -164,7 +183,8 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
         while ((inner_res > tol) && (inner < restart)){
             T *wj = W + (size_t) inner * ldw;
             if ((rc = halo(wj)) != HB_OK) return rc;
-            if ((rc = hb_spmv_internal(ctx, A, wj, t, nullptr)) != HB_OK) return rc;                         // t = A w_j ; r = P^-1 t
+            if ((rc = hb_spmv_internal(ctx, A, wj, ta, nullptr)) != HB_OK) return rc;                        // t = A w_j ; r = P^-1 t
+            if (precon.fn && (rc = precon(ta, t)) != HB_OK) return rc;
             total++;
             const int k = inner + 1;
             if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, ldw, t, hdev, nullptr)) != HB_OK) return rc;
@@ -242,7 +262,7 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
         for (int j = 0; j < batch; j++, it++){
             const int parity = (int) (it & 1);
             if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;               // Ap = A p ; <p,Ap>
-            if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev)) != HB_OK) return rc;
+            if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev, 0)) != HB_OK) return rc;
             // iteration `it` turns the operator-application counter into it + 2 (setup leaves it at 1)
             const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
             if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, it_now, r, p, x)) != HB_OK) return rc;
@@ -256,6 +276,74 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = hstat->iterations;
     if (res) *res = hstat->rnorm;
+    return HB_OK;
+}
+
+// Preconditioned CG: the recurrence of solve_cg_core (hex/solvers/hala_solvers_cg.hpp:92-156) with the caller's preconditioner between
+// our kernels.  Per iteration: SpMV + <p,Ap> | r -= a Ap, ||r||, stop test | z = P^-1 r (caller) | <r,z> | x += a p, p = z + b p:
+// four launches of ours + whatever the preconditioner enqueues, all scalars on the device.  The host runs at most `lag` iterations
+// ahead of the device and reads the mapped status without ever stalling the stream; iterations enqueued past the stop are skipped
+// by the done flag (the caller's preconditioner still runs for them, on a residual that no longer changes).
+int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, hb_precon_fn precon_fn, void *user, int *iters, double *res){
+    if (!precon_fn) return hb_cg(ctx, A, b, x, tol, max_iter, iters, res);
+    HB_ARG(ctx && A && b && x, "null");
+    HB_ARG(A->rows == A->cols, "CG needs a square matrix");
+    const int n = A->rows, dtype = A->dtype;
+    const size_t es = hb_dtype_size(dtype);
+    if (n == 0){ if (iters) *iters = 1; if (res) *res = 0; return HB_OK; }
+    precon_call precon; precon.fn = precon_fn; precon.user = user;
+    int rc;
+    const size_t vec_bytes = ((es * (size_t) n + 255) / 256) * 256;
+    void *arena = nullptr;
+    if ((rc = hb_ctx_workspace(ctx, 4 * vec_bytes + 256, &arena)) != HB_OK) return rc;       // r | z | p | Ap | state
+    char *base = (char*) arena;
+    void *r = base, *z = base + vec_bytes, *p = base + 2 * vec_bytes, *Ap = base + 3 * vec_bytes, *state = base + 4 * vec_bytes;
+    void *pap = (char*) state + hb_cg_state_pap_offset(dtype);
+    const int *done_flag = reinterpret_cast<const int*>((char*) state + hb_cg_state_done_offset(dtype));
+    cg_host_status_h *hstat = reinterpret_cast<cg_host_status_h*>(reinterpret_cast<char*>(ctx->hscalars) + 256);
+    void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 256;
+    hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
+
+    if ((rc = hb_spmv_internal(ctx, A, x, Ap, nullptr)) != HB_OK) return rc;                                  // p = A x ; r = b - p   (cg:108-111)
+    if ((rc = hb_cg_setup_internal(ctx, dtype, n, state, tol, max_iter, b, Ap, r, p, hstat_dev)) != HB_OK) return rc;
+    if ((rc = precon(r, z)) != HB_OK) return rc;                                                              // z = P^-1 r            (cg:116)
+    if ((rc = hb_pcg_dot_internal(ctx, dtype, n, state, 0, r, z, p)) != HB_OK) return rc;                     // p = z ; zr = <r,z>    (cg:121-123)
+
+    constexpr int lag = 2, nev = 4;
+    cudaEvent_t ev[nev];
+    for (int k = 0; k < nev; k++) ev[k] = nullptr;
+    struct ev_guard { cudaEvent_t *e; int n; ~ev_guard(){ for (int k = 0; k < n; k++) if (e[k]) cudaEventDestroy(e[k]); } } guard{ev, nev};
+    for (int k = 0; k < nev; k++) HB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    for (long long it = 0; ; it++){
+        const int parity = (int) (it & 1);
+        if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;                   // Ap = A p ; <p,Ap>
+        if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev, 1)) != HB_OK) return rc;
+        if ((rc = precon(r, z)) != HB_OK) return rc;
+        if ((rc = hb_pcg_dot_internal(ctx, dtype, n, state, parity ^ 1, r, z, nullptr)) != HB_OK) return rc;  // new <r,z>
+        const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
+        if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, it_now, z, p, x)) != HB_OK) return rc;
+        HB_CUDA(cudaEventRecord(ev[it % nev], ctx->stream));
+        if (hstat->done) break;                                                                               // a glance at the mapped status: no stall
+        if (it >= lag){
+            HB_CUDA(cudaEventSynchronize(ev[(it - lag) % nev]));
+            if (hstat->done) break;
+        }
+    }
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iters) *iters = hstat->iterations;
+    if (res) *res = hstat->rnorm;
+    return HB_OK;
+}
+
+// GMRES(m) with the caller's (left) preconditioner: r = P^-1 (A w_j), as solve_gmres applies it (hala_solvers_gmres.hpp:176,186)
+int hb_pgmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, hb_precon_fn precon_fn, void *user,
+              int *iters, double *res){
+    HB_ARG(ctx && A && b && x, "null");
+    HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
+    HB_ARG(restart >= 1, "restart must be positive");
+    if (A->rows == 0){ if (iters) *iters = 0; if (res) *res = 0; return HB_OK; }
+    precon_call precon; precon.fn = precon_fn; precon.user = user;
+    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, nullptr, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res, precon); });
     return HB_OK;
 }
 
@@ -275,8 +363,26 @@ int hb_dist_gmres(hb_dist *dist, const hb_csr *A, const void *b, void *x, double
     HB_ARG(A->rows == hb_dist_owned(dist) && A->cols == hb_dist_owned(dist) + hb_dist_ghosts(dist), "matrix shape does not match the exchange plan");
     // halo of the basis vectors and the all-reduced Gram-Schmidt coefficients go over peer memory when the ranks can map each other
     { int prc = hb_dist_prepare_transport(dist, A->dtype); if (prc != HB_OK) return prc; }
-    HB_DISPATCH(A->dtype, { return gmres_typed<T>(ctx, dist, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
-    return HB_OK;
+    // over peer memory a wait that times out poisons the sums with NaN, which ends the solve on every rank: keep x0 so that the
+    // solve can be redone over NCCL (agreed by all ranks in hb_dist_finish_transport)
+    int transport = HB_TRANSPORT_NCCL;
+    hb_dist_transport(dist, &transport);
+    dev_buffer x0;
+    const size_t xbytes = hb_dtype_size(A->dtype) * (size_t) A->rows;
+    if (transport == HB_TRANSPORT_PEER){
+        int rc = x0.alloc(xbytes); if (rc != HB_OK) return rc;
+        HB_CUDA(cudaMemcpyAsync(x0.p, x, xbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    int rc = HB_OK;
+    HB_DISPATCH(A->dtype, { rc = gmres_typed<T>(ctx, dist, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
+    if (rc != HB_OK || transport != HB_TRANSPORT_PEER) return rc;
+    int timed_out = 0;
+    if ((rc = hb_dist_finish_transport(dist, &timed_out)) != HB_OK) return rc;
+    if (timed_out){
+        HB_CUDA(cudaMemcpyAsync(x, x0.p, xbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        HB_DISPATCH(A->dtype, { rc = gmres_typed<T>(ctx, dist, A, (const T*) b, (T*) x, tol, max_outer, restart, cproj, iters, res); });
+    }
+    return rc;
 }
 
 }

@@ -21,6 +21,7 @@
 #include "hb_spmv_pipe.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------ analysis
 __global__ void csr_analyse_kernel(int rows, const int *pntr, int *stats){
@@ -262,15 +263,15 @@ static int launch_tiles(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_a
     int grid = std::min(ntiles, ctx->num_sms * per_sm);
     if (grid < 1) grid = 1;
     if (A->vec_aligned){
-        static bool attr_set = false;
+        static per_device_flag attr_set;
         auto k = spmv_tiles_kernel<T, ROWS, true, DOT>;
-        if (!attr_set){ HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_set = true; }
+        if (attr_set.first_time(ctx->device)) HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         k<<<grid, ROWS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                              ctx->partials, ctx->tickets + 1, dot_out, skip);
     }else{
-        static bool attr_set = false;
+        static per_device_flag attr_set;
         auto k = spmv_tiles_kernel<T, ROWS, false, DOT>;
-        if (!attr_set){ HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr_set = true; }
+        if (attr_set.first_time(ctx->device)) HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         k<<<grid, ROWS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                              ctx->partials, ctx->tickets + 1, dot_out, skip);
     }
@@ -311,7 +312,9 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
                                                             A->pipe_contiguous ? A->cta_rows[CFG] : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip,
                                                             (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols,
-                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0, (size_t) 0);
+                                                            DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0, (size_t) 0,
+                                                            (DOT && ctx->peer_hook && !A->pipe_contiguous) ? ctx->peer_trot : 0,
+                                                            (DOT && ctx->peer_hook && !A->pipe_contiguous) ? ctx->peer_twait : 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -332,16 +335,15 @@ static int launch_pipe_mm_cfg(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t 
     using C = pipe_cfg<CFG>;
     const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, false, NBP>;
-    static bool configured = false;
-    if (!configured){
+    static per_device_flag configured;
+    if (configured.first_time(ctx->device)){
         HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
     scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, Bt, Ct, one, zero,
-                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct, (size_t) 0);
+                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct, (size_t) 0, 0, 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -365,8 +367,9 @@ static int launch_pipe_lpc_cfg(hb_ctx *ctx, const hb_csr *A, int nb, const T *B,
     using C = pipe_cfg<CFG>;
     const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, false, NBP, true>;
-    static int occ = -1;
-    if (occ < 0){
+    static int occ_by_device[256];                       // 0: not asked yet on that device
+    int &occ = occ_by_device[(unsigned) ctx->device & 255u];
+    if (occ <= 0){
         HB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int n = 0;
@@ -377,7 +380,7 @@ static int launch_pipe_lpc_cfg(hb_ctx *ctx, const hb_csr *A, int nb, const T *B,
     const long long ntiles = ((long long) A->rows + tile_rows - 1) / tile_rows;
     const int grid = (int) std::min<long long>(ntiles, (long long) ctx->num_sms * occ);
     k<<<grid, C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, B, Cm, alpha, beta,
-                                               nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, nb, A->cols, nullptr, 0ull, sxr, ldc, sxc);
+                                               nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, nb, A->cols, nullptr, 0ull, sxr, ldc, sxc, 0, 0);
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -503,6 +506,51 @@ int hb_spmv_internal(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, const
     return HB_OK;
 }
 
+// ---- row-partitioned runs: which tiles of the streaming kernel reference ghost columns (columns >= rows of the local matrix)
+__global__ void csr_tile_ghost_kernel(int rows, const int * __restrict__ pntr, const int * __restrict__ indx, int tile_rows, unsigned char *flags){
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x){
+        const int rs = pntr[r], re = pntr[r + 1];
+        bool g = false;
+        for (int j = rs; j < re; j++) g = g || (indx[j] >= rows);
+        if (g) flags[r / tile_rows] = 1;                    // same value from every writer
+    }
+}
+// trot: tiles to rotate the round-robin sweep by (= length of the leading run of ghost-touching tiles, so that the sweep starts
+// at the first interior tile and the leading boundary block comes last); twait: first position of the rotated order whose tile
+// touches a ghost column.  1-D row blocks of a stencil: [lower face | interior | upper face] -> interior, upper face, lower face.
+int hb_csr_halo_order(hb_ctx *ctx, const hb_csr *A, int *trot, int *twait){
+    if (!A->halo_state){
+        A->halo_trot = 0; A->halo_twait = 0;
+        if (hb_spmv_variant(A) == 3 && !A->pipe_contiguous && A->cols > A->rows && A->rows > 0){
+            const int threads = A->pipe_cfg == 0 ? pipe_cfg<0>::THREADS : pipe_cfg<1>::THREADS;
+            const int tile_rows = threads / A->tpr;
+            const int ntiles = (A->rows + tile_rows - 1) / tile_rows;
+            unsigned char *flags = nullptr;
+            HB_CUDA(cudaMalloc((void**) &flags, (size_t) ntiles));
+            std::vector<unsigned char> h((size_t) ntiles);
+            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t) ntiles, ctx->stream);
+            if (e == cudaSuccess){
+                csr_tile_ghost_kernel<<<hb_grid_for(ctx, (size_t) A->rows, 256, 8), 256, 0, ctx->stream>>>(A->rows, A->pntr, A->indx, tile_rows, flags);
+                ctx->launches++;
+                e = cudaMemcpyAsync(h.data(), flags, (size_t) ntiles, cudaMemcpyDeviceToHost, ctx->stream);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(flags);
+            if (e != cudaSuccess) return hb_cuda_fail(e, "halo order analysis");
+            int rot = 0;
+            while (rot < ntiles && h[(size_t) rot]) rot++;
+            if (rot < ntiles){                              // at least one interior tile
+                int w = 0;
+                while (w < ntiles && !h[(size_t) ((w + rot) % ntiles)]) w++;
+                A->halo_trot = rot; A->halo_twait = w;      // w == ntiles: nothing touches a ghost, nobody waits
+            }
+        }
+        A->halo_state = 1;
+    }
+    *trot = A->halo_trot; *twait = A->halo_twait;
+    return HB_OK;
+}
+
 extern "C" {
 
 int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int *pntr, const int *indx, const void *vals, hb_csr **out){
@@ -516,8 +564,6 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     A->pntr = pntr; A->indx = indx; A->vals = vals;
     A->vec_aligned = aligned16p(indx) && aligned16p(vals);
     A->tc = hb_tcache_new();
-    A->band_slot = new hb_band*[1];
-    A->band_slot[0] = nullptr;
     A->mean_row_nnz = rows > 0 ? (double) nnz / rows : 0.0;
     // one-time analysis: longest row (one tiny kernel, one 4-byte read-back) — decides the tile shape and the tile-to-CTA map below
     A->stats_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->dscalars) + 2048);
@@ -574,7 +620,6 @@ int hb_csr_destroy(hb_csr *csr){
     if (!csr) return HB_OK;
     for (int c = 0; c < 2; c++) if (csr->cta_rows[c]) cudaFree(csr->cta_rows[c]);
     hb_tcache_delete(csr->tc);
-    if (csr->band_slot){ hb_band_delete(csr->band_slot[0]); delete[] csr->band_slot; }
     delete csr;
     return HB_OK;
 }

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
                                                             void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
-                                                            const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy, size_t sxc){
+                                                            const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy, size_t sxc,
+                                                            int trot, int twait){
     constexpr int ROWS = THREADS / TPR;
     constexpr int CAP  = THREADS * pipe_slots<T>();
     constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
@@ -72,12 +73,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     __shared__ T        red[32];
 
     if (skip_flag && *skip_flag) return;
-    // row-partitioned run over peer memory: the ghost entries of x are being stored by the neighbours' direction kernels;
-    // wait for their flags before the first gather (the matrix stream itself does not depend on them)
-    if (pv){
-        if (threadIdx.x < 32) peer_halo_wait(pv, epoch);
-        __syncthreads();
-    }
+    // Row-partitioned run over peer memory: the ghost entries of x are being stored by the neighbours' direction kernels.  Only
+    // rows that reference ghost columns depend on them, so the sweep is rotated by `trot` tiles (round-robin map) to start
+    // behind the leading block of such rows and each CTA waits for the neighbours' flags right before its first tile at or beyond
+    // virtual position `twait` (the first tile of the rotated order that touches a ghost): interior rows run while the halo is
+    // still in flight, CTAs that own no boundary tile never wait.  trot = twait = 0 is a wait before the first gather.
+    bool halo_pending = (pv != nullptr);
 
     const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
     const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
@@ -109,13 +110,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
         // two of them per issue; a dependent global load there would put a DRAM round trip on every step's critical path
         // (all warps meet at the per-step barrier), so the ring is refilled 32 entries at a time with cp.async by the last
         // warp, a whole 16 steps before the data is waited for and 30 before it is used.
-        auto bound_src  = [&](int j){ return pntr + min((long long) (tile_begin + (long long) j * tstride) * ROWS, (long long) rows); };
-        auto bound_src1 = [&](int j){ return pntr + min((long long) (tile_begin + (long long) j * tstride + 1) * ROWS, (long long) rows); };
+        auto phys = [&](int j){ int t = tile_begin + j * tstride + trot; return t >= ntiles_all ? t - ntiles_all : t; };   // tile of step j
+        auto bound_src  = [&](int j){ return pntr + min((long long) phys(j) * ROWS, (long long) rows); };
+        auto bound_src1 = [&](int j){ return pntr + min(((long long) phys(j) + 1) * ROWS, (long long) rows); };
         for (int j = tid; j < BND && j < ntile; j += THREADS){ bnd[j] = __ldg(bound_src(j)); bnd1[j] = __ldg(bound_src1(j)); }
         __syncthreads();
         auto issue = [&](int k, int b0, int b1){             // thread 0 only; b0,b1 = non-zero bounds of tile k
             const int s = k % STAGES;
-            const int r0 = (tile_begin + k * tstride) * ROWS;
+            const int r0 = phys(k) * ROWS;
             T *sv = stage_vals(s); int *sc = stage_cols(s); int *sp = stage_ptr(s);
             // pntr slice [r0, r0 + PSL) clipped to the array; ragged end by hand
             const int pend = min(r0 + PSL, rows + 1);
@@ -156,8 +158,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                     cp_async_wait_all();                        // published to thread 0 by this step's closing barrier
                 }
             }
+            if (halo_pending && tile_begin + k * tstride >= twait){        // block-uniform
+                if (tid < 32) peer_halo_wait(pv, epoch);
+                __syncthreads();
+                halo_pending = false;
+            }
             mbar_wait(full + s, (uint32_t) ((k / STAGES) & 1));
-            const int r0 = (tile_begin + k * tstride) * ROWS;
+            const int r0 = phys(k) * ROWS;
             const int myrow = r0 + grp;
             const int *sp = stage_ptr(s);
             const int a0 = stage_a0[s];
@@ -356,7 +363,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             if (tid == 0){ *dot_out = total; red[0] = total; }
             if (pv){                                            // hand this rank's partial to every peer (hb_peer.cuh)
                 __syncthreads();
-                if (tid < 32) peer_publish<T>(pv, HB_PEER_CH_PAP, epoch, red[0]);
+                // a halo wait of this launch timed out: the product was formed from stale ghosts — hand out NaN, which stops
+                // every rank at the next stop test instead of letting the iteration run on with wrong data
+                const bool poisoned = *reinterpret_cast<volatile int*>(&pv->mail[pv->rank]->error) != 0;
+                T out = red[0];
+                if (poisoned) out = from_real<T>((real_t<T>) __longlong_as_double(0x7ff8000000000000LL));
+                if (tid < 32) peer_publish<T>(pv, HB_PEER_CH_PAP, epoch, out);
             }
         }
     }

@@ -23,6 +23,8 @@ DIST_SIGNATURES = {
     "hb_dist_halo_exchange_nccl": (_i, [_vp, _i, _vp]),
     "hb_dist_allreduce_sum_nccl": (_i, [_vp, _i, _vp, _i]),
     "hb_dist_prepare_transport": (_i, [_vp, _i]),
+    "hb_dist_finish_transport": (_i, [_vp, _pi]),
+    "hb_dist_debug_info": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _pi, _pi]),
     "hb_dist_cg": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi, C.POINTER(_d)]),
     "hb_dist_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "hb_dist_gmres": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _pi, C.POINTER(_d)]),
@@ -71,6 +73,13 @@ class Communicator:
         check(lib.hb_dist_transport(self.h, C.byref(t)), "hb_dist_transport")
         return "peer" if t.value == 1 else "nccl"
 
+    def debug_info(self):
+        """sequence numbers of the peer protocol (equal on all ranks between solves), solves redone over NCCL after a peer
+        time-out, start-of-solve agreements that found the ranks' sequence numbers different"""
+        ep, vep, fb, rep = C.c_ulonglong(0), C.c_ulonglong(0), C.c_int(0), C.c_int(0)
+        check(lib.hb_dist_debug_info(self.h, C.byref(ep), C.byref(vep), C.byref(fb), C.byref(rep)), "hb_dist_debug_info")
+        return {"epoch": ep.value, "vepoch": vep.value, "peer_fallbacks": fb.value, "epoch_repairs": rep.value}
+
     def gmres(self, csr, b_ptr, x_ptr, tol, max_outer, restart, cproj=0):
         it, res = C.c_int(0), C.c_double(0)
         check(lib.hb_dist_gmres(self.h, csr.h, b_ptr, x_ptr, float(tol), int(max_outer), int(restart), int(cproj), C.byref(it), C.byref(res)), "hb_dist_gmres")
@@ -118,6 +127,24 @@ def run_bench(args, slab, ClockSampler, measured_peak):
     dist.init_process_group("nccl", device_id=torch.device(dev))
     e = hb.gpu_engine(local)
     comm = Communicator(e, rank, world)
+    try:
+        _run_bench_body(args, e, comm, rank, world, local, dev, ClockSampler, measured_peak)
+    except BaseException as ex:
+        # what bench.py prints for a failing rank: transport and sequence numbers of the peer protocol included
+        try:
+            ex.hb_diag = dict(comm.debug_info(), transport=comm.transport())
+        except Exception:
+            pass
+        raise
+    dist.barrier()
+    del comm
+    dist.destroy_process_group()
+
+
+def _run_bench_body(args, e, comm, rank, world, local, dev, ClockSampler, measured_peak):
+    import torch
+    import torch.distributed as dist
+    from . import matgen as mg
     peak, peak_src = measured_peak()
     n = args.grid
     prob = build_local_problem(e, comm, "lap3d7", n, dev)
@@ -223,8 +250,6 @@ def run_bench(args, slab, ClockSampler, measured_peak):
                              "algorithmic_bytes_per_launch": Bk, "us_per_launch": kms * 1e3, "share_of_step": kms / (ms / args.steps),
                              "how": "CUDA events around 30 back-to-back launches per rank, max over ranks"},
                 "cpu_baseline": None,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+                "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+                "transport_diag": dict(comm.debug_info(), transport=comm.transport())}
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    del comm
-    dist.destroy_process_group()

@@ -12,16 +12,27 @@ class gpu_vector{
 public:
     using value_type = T;
 
-    gpu_vector(int deviceid = 0) : gpu(deviceid), count(0), ptr(nullptr){ check_gpu_type<T>(); }
-    gpu_vector(size_t num_entries, int deviceid) : gpu(deviceid), count(0), ptr(nullptr){ check_gpu_type<T>(); allocate(num_entries); }
-    gpu_vector(gpu_vector<T> const &other) : gpu(other.gpu), count(0), ptr(nullptr){
+    gpu_vector(int deviceid = 0) : gpu(deviceid), count(0), ptr(nullptr), owner(true){ check_gpu_type<T>(); }
+    gpu_vector(size_t num_entries, int deviceid) : gpu(deviceid), count(0), ptr(nullptr), owner(true){ check_gpu_type<T>(); allocate(num_entries); }
+    gpu_vector(gpu_vector<T> const &other) : gpu(other.gpu), count(0), ptr(nullptr), owner(true){
         allocate(other.count);
         gpu_copy_n<copy_direction::device2device>(static_cast<T const*>(other.ptr), count, ptr);
     }
-    gpu_vector(gpu_vector<T> &&other) : gpu(other.gpu), count(std::exchange(other.count, 0)), ptr(std::exchange(other.ptr, nullptr)){}
+    gpu_vector(gpu_vector<T> &&other)
+        : gpu(other.gpu), count(std::exchange(other.count, 0)), ptr(std::exchange(other.ptr, nullptr)), owner(std::exchange(other.owner, true)){}
     ~gpu_vector(){ clear(); }
 
-    void clear(){ gpu_free(ptr); ptr = nullptr; count = 0; }
+    //! extension (hala_gpu_solvers.hpp): a gpu_vector over device memory somebody else owns — the work arrays of the fused solvers as the
+    //! caller's preconditioner sees them.  Same-size operations (vcopy into it, copy-assignment, ilu.apply) write through; resizing
+    //! it to another size detaches it (the vector then owns fresh memory and the borrowed array is left alone).
+    static gpu_vector<T> view(int deviceid, T *device_array, size_t num_entries){
+        gpu_vector<T> v(deviceid);
+        v.ptr = device_array; v.count = num_entries; v.owner = false;
+        return v;
+    }
+    bool owns_memory() const{ return owner; }
+
+    void clear(){ if (owner) gpu_free(ptr); ptr = nullptr; count = 0; owner = true; }
 
     void operator =(gpu_vector<T> const &other){
         if (this == &other) return;
@@ -34,12 +45,13 @@ public:
     }
     void operator =(gpu_vector<T> &&other){
         gpu_vector<T> tmp(std::move(other));
-        std::swap(gpu, tmp.gpu); std::swap(count, tmp.count); std::swap(ptr, tmp.ptr);
+        std::swap(gpu, tmp.gpu); std::swap(count, tmp.count); std::swap(ptr, tmp.ptr); std::swap(owner, tmp.owner);
     }
 
     void resize(size_t new_size){
         if (new_size == count) return;
-        gpu_free(ptr); ptr = nullptr;
+        if (owner) gpu_free(ptr);
+        ptr = nullptr; owner = true;
         allocate(new_size);
     }
     template<class VectorLike> void load(VectorLike const &cpu_data){
@@ -80,6 +92,7 @@ private:
     int gpu;
     size_t count;
     T *ptr;
+    bool owner;
 };
 
 template<class VectorLike>

@@ -34,7 +34,7 @@ typedef struct hb_csr hb_csr;
 typedef struct hb_tri hb_tri;   /* replaces cusparseSpMatDescr_t + the cached SpSV/SpSM analyses of gpu_triangular_matrix (gpu/hala_cuda_sparse_triangular.hpp:38-110) */   /* replaces cusparseSpMatDescr_t + cached buffer sizes of gpu_sparse_matrix (gpu/hala_cuda_sparse_general.hpp:191-375) */
 
 enum { HB_F32 = 0, HB_F64 = 1, HB_C32 = 2, HB_C64 = 3 };
-enum { HB_OK = 0, HB_ERR_CUDA = 1, HB_ERR_ARG = 2, HB_ERR_ALLOC = 3, HB_ERR_UNSUPPORTED = 4, HB_ERR_NCCL = 5, HB_ERR_NOT_CONVERGED = 6 };
+enum { HB_OK = 0, HB_ERR_CUDA = 1, HB_ERR_ARG = 2, HB_ERR_ALLOC = 3, HB_ERR_UNSUPPORTED = 4, HB_ERR_NCCL = 5, HB_ERR_NOT_CONVERGED = 6, HB_ERR_CALLBACK = 7 };
 enum { HB_POINTER_HOST = 0, HB_POINTER_DEVICE = 1 };
 enum { HB_H2D = 0, HB_D2H = 1, HB_D2D = 2 };
 
@@ -184,6 +184,20 @@ int hb_xpby(hb_ctx *ctx, int dtype, int n, const void *r, const void *b_dev, voi
 int hb_cg(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, int *iters, double *res);
 int hb_gmres(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_outer, int restart, int cproj,
              int *iters, double *res);
+
+
+/* ---- the same solvers with the caller's preconditioner (hala::preconditioner, hex/solvers/hala_solvers_core.hpp:75-118) ----
+ * precon(user, in, out) must enqueue out = P^-1 in on the context's stream (device pointers, n scalars of the matrix type, never
+ * aliased) and return 0; any other value aborts the solve with HB_ERR_CALLBACK.  It is called once per operator application; after
+ * the device-side stop test fires it may still be called for a few iterations that are skipped (its output is then ignored).
+ * hb_pcg   : solve_cg_core with z = P^-1 r (hala_solvers_cg.hpp:116,140-150): four launches of this library per iteration plus the
+ *            preconditioner's own, no host synchronisation that stalls the stream.  precon == NULL is hb_cg.
+ * hb_pgmres: solve_gmres with r = P^-1 (A w) (hala_solvers_gmres.hpp:176,186).  precon == NULL is hb_gmres. */
+typedef int (*hb_precon_fn)(void *user, const void *in_dev, void *out_dev);
+int hb_pcg(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_iter, hb_precon_fn precon, void *user,
+           int *iters, double *res);
+int hb_pgmres(hb_ctx *ctx, const hb_csr *csr, const void *b, void *x, double tol, int max_outer, int restart, int cproj,
+              hb_precon_fn precon, void *user, int *iters, double *res);
 
 #ifdef __cplusplus
 }

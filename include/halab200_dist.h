@@ -47,6 +47,13 @@ int hb_dist_allreduce_sum(hb_dist *dist, int dtype, void *dev_scalars, int count
 int hb_dist_allreduce_sum_nccl(hb_dist *dist, int dtype, void *dev_scalars, int count);
 /* collective: brings the peer transport up for `dtype` when all ranks can map each other (hb_dist_cg / hb_dist_gmres call it) */
 int hb_dist_prepare_transport(hb_dist *dist, int dtype);
+/* collective, closes a sequence of hb_dist_halo_exchange / hb_dist_allreduce_sum calls that ran over peer memory: *timed_out = 1 on ALL
+ * ranks when a wait on a peer's flag gave up on any rank (the sums were poisoned with NaN); the communicator then drops to NCCL for good
+ * and the caller redoes its work.  hb_dist_cg / hb_dist_gmres do this themselves. */
+int hb_dist_finish_transport(hb_dist *dist, int *timed_out);
+/* diagnostics: the peer protocol's sequence numbers (equal on all ranks after every solve), how many solves fell back from peer memory
+ * to NCCL after a time-out, and how many times the start-of-solve agreement found the ranks' sequence numbers different */
+int hb_dist_debug_info(const hb_dist *dist, unsigned long long *epoch, unsigned long long *vepoch, int *peer_fallbacks, int *epoch_repairs);
 
 /* Row-partitioned CG.  csr = local rows with columns renumbered to [owned | ghosts] (cols == n_owned + n_ghost);
  * b, x = owned parts.  Same recurrence, counter and stop test as hb_cg; per iteration: halo exchange of p, SpMV fused with

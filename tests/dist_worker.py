@@ -10,6 +10,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _expect(name, value):
+    want = os.environ.get(name)
+    if want is None:
+        return
+    if want.endswith("+"):
+        assert value >= int(want[:-1]), (name, want, value)
+    else:
+        assert value == int(want), (name, want, value)
+
+
+def check_sequence_numbers(comm, dist, torch, dev, world, final=False):
+    """the peer protocol's sequence numbers after a solve: equal on all ranks (unless the test asked for round-1 counting);
+    at the end, the fall-back / repair counters the test expects"""
+    info = comm.debug_info()
+    if os.environ.get("HB_DEBUG_EPOCH_RULE") != "host":
+        t = torch.tensor([info["epoch"], info["vepoch"]], dtype=torch.int64, device=dev)
+        lst = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(lst, t)
+        assert all(torch.equal(q, t) for q in lst), ("sequence numbers differ between ranks", [q.tolist() for q in lst])
+    if final:
+        _expect("HB_EXPECT_FALLBACKS", info["peer_fallbacks"])
+        _expect("HB_EXPECT_REPAIRS", info["epoch_repairs"])
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -55,6 +79,7 @@ def main():
         want = os.environ.get("HB_EXPECT_TRANSPORT")
         if want:
             assert comm.transport() == want, (comm.transport(), want)
+        check_sequence_numbers(comm, dist, torch, dev, world)
         # --- the same SpMV again now that the transport of this plan is up (peer runs: halo pushed into the neighbours' exchange buffers)
         x_ext[n_owned:] = 0
         y.zero_()
@@ -79,8 +104,9 @@ def main():
     xo, ito = orc.gmres(p, i, v, mg.rhs(N), tol, 20)
     assert abs(it - ito) <= 2, (it, ito)
     assert np.max(np.abs(x.cpu().numpy() - xo[lo:hi])) < 1e-6
+    check_sequence_numbers(comm, dist, torch, dev, world, final=True)
     if rank == 0:
-        print(f"dist ok: gmres {name}:{n} world={world} {it} its (oracle {ito})", flush=True)
+        print(f"dist ok: gmres {name}:{n} world={world} {it} its (oracle {ito}) {comm.debug_info()}", flush=True)
     del prob
     dist.barrier()
     del comm

@@ -13,6 +13,38 @@ TRANSPORTS = {
     "peer-helpers": {"HB_PEER_FUSED_SPMV": "0"},    # peer memory, halo wait / publish as 1-warp kernels around the SpMV
     "nccl": {"HB_DIST_PEER": "0"},                  # ncclSend/Recv + ncclAllReduce
 }
+# The peer protocol's sequence numbers ("epochs") must be equal on all ranks.  Round 1 let every host count the batches it had
+# enqueued, which depends on WHEN that host saw the done flag: a rank one batch ahead waits for flags its peers never send, every
+# wait runs into its time-out and the solve fails (the N = 8 bench failure of round 1).  HB_DEBUG_EPOCH_SKEW makes the odd ranks
+# count one batch more, as a late host would have; the three cases walk from the fixed protocol back to the round-1 one:
+SKEW_CASES = {
+    # agreed advance (iterations executed, identical on all ranks): the skew never reaches the sequence numbers
+    "agreed-advance": ({"HB_DEBUG_EPOCH_SKEW": "1"}, {"HB_EXPECT_TRANSPORT": "peer", "HB_EXPECT_FALLBACKS": "0", "HB_EXPECT_REPAIRS": "0"}),
+    # per-host counting as in round 1, but every solve starts with an all-reduce(MAX) of the sequence numbers: repaired
+    "host-count+agree": ({"HB_DEBUG_EPOCH_SKEW": "1", "HB_DEBUG_EPOCH_RULE": "host"},
+                         {"HB_EXPECT_TRANSPORT": "peer", "HB_EXPECT_FALLBACKS": "0", "HB_EXPECT_REPAIRS": "1+"}),
+    # round 1 as it was: waits time out (shortened to 100 ms), every rank sees NaN, all agree to redo the solve over NCCL
+    "round1": ({"HB_DEBUG_EPOCH_SKEW": "1", "HB_DEBUG_EPOCH_RULE": "host", "HB_DEBUG_NO_EPOCH_AGREE": "1", "HB_PEER_TIMEOUT_MS": "100"},
+               {"HB_EXPECT_TRANSPORT": "nccl", "HB_EXPECT_FALLBACKS": "1+", "HB_EXPECT_REPAIRS": "0"}),
+}
+
+
+def _run_worker(world, port, env_extra, timeout=600):
+    env = dict(os.environ, **env_extra)
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")], capture_output=True, text=True, timeout=timeout, env=env)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(SKEW_CASES))
+def test_peer_sequence_numbers_survive_host_skew(case):
+    import hala_b200 as hb
+    if hb.gpu_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    inject, expect = SKEW_CASES[case]
+    r = _run_worker(2, 29700 + list(SKEW_CASES).index(case), dict(inject, **expect))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    assert r.stdout.count("dist ok") == 4, r.stdout[-2000:]
 
 
 @pytest.mark.gpu
@@ -23,8 +55,7 @@ def test_row_partitioned_spmv_and_cg(world, transport):
     if hb.gpu_device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29600 + world + 16 * list(TRANSPORTS).index(transport)
-    env = dict(os.environ, **TRANSPORTS[transport], HB_EXPECT_TRANSPORT=transport.split("-")[0])
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    expect = {"HB_EXPECT_TRANSPORT": transport.split("-")[0], "HB_EXPECT_FALLBACKS": "0", "HB_EXPECT_REPAIRS": "0"}
+    r = _run_worker(world, port, dict(TRANSPORTS[transport], **expect))
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert r.stdout.count("dist ok") == 4, r.stdout[-2000:]
