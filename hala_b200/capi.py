@@ -36,6 +36,8 @@ SIGNATURES = {
     "hb_ctx_get_pointer_mode": (_i, [_vp, _pi]),
     "hb_ctx_launch_count": (_i, [_vp, C.POINTER(C.c_longlong)]),
     "hb_ctx_trim": (_i, [_vp]),
+    "hb_ctx_profile": (_i, [_vp, _i]),
+    "hb_ctx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "hb_timer_start": (_i, [_vp]),
     "hb_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "hb_malloc": (_i, [_vp, _sz, _pvp]),

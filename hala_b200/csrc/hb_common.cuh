@@ -10,7 +10,18 @@
 // ----------------------------------------------------------------------------------------------------------------
 // context / matrix objects behind the opaque C handles
 // ----------------------------------------------------------------------------------------------------------------
+// per-kernel CUDA-event timing of the solver loops (hb_ctx_profile): events on the context's stream around every launch of the
+// first MAXIT iterations of a solve, read after the solve's final synchronisation.  Off by default.
+struct hb_prof {
+    static constexpr int SLOTS = 4, MAXIT = 512;
+    int on = 0;
+    cudaEvent_t ev[MAXIT * (SLOTS + 1)] = {};
+    int marked = 0;                     // iterations of the current solve that carry events
+    double ms[SLOTS] = {0, 0, 0, 0};
+    long long n[SLOTS] = {0, 0, 0, 0};
+};
 struct hb_ctx {
+    hb_prof *prof = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;      // legacy default stream unless hb_ctx_set_stream
     int pointer_mode = HB_POINTER_HOST;
@@ -34,6 +45,11 @@ struct hb_ctx {
     int peer_trot = 0, peer_twait = 0;  // tile rotation / first tile that needs the halo (hb_spmv_pipe.cuh), from hb_csr_halo_order
 };
 int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr);
+// no-ops unless profiling is on: event k of iteration `it` (k = 0 before the first kernel, k = j + 1 after kernel j); collect after the
+// stream is synchronised, counting the first `valid_iterations` (the ones the done flag did not skip) over `slots` kernels
+void hb_prof_begin(hb_ctx *ctx);
+void hb_prof_mark(hb_ctx *ctx, long long it, int k);
+void hb_prof_collect(hb_ctx *ctx, long long valid_iterations, int slots);
 
 static constexpr size_t HB_PARTIAL_BYTES = 4u << 20;   // 4 MiB: (blocks x up-to-64 columns x 16 B) fits for grid <= 4096
 static constexpr int    HB_NUM_TICKETS   = 64;

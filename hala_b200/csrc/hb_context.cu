@@ -88,6 +88,30 @@ int hb_ctx_workspace(hb_ctx *ctx, size_t bytes, void **ptr){
     return HB_OK;
 }
 
+// ---- per-kernel event timing of the solver loops (hb_ctx_profile)
+void hb_prof_begin(hb_ctx *ctx){ if (ctx->prof && ctx->prof->on) ctx->prof->marked = 0; }
+void hb_prof_mark(hb_ctx *ctx, long long it, int k){
+    hb_prof *p = ctx->prof;
+    if (!p || !p->on || it >= hb_prof::MAXIT || k > hb_prof::SLOTS) return;
+    cudaEvent_t &e = p->ev[it * (hb_prof::SLOTS + 1) + k];
+    if (!e && cudaEventCreate(&e) != cudaSuccess){ cudaGetLastError(); e = nullptr; return; }
+    cudaEventRecord(e, ctx->stream);
+    if (it + 1 > p->marked) p->marked = (int) (it + 1);
+}
+void hb_prof_collect(hb_ctx *ctx, long long valid_iterations, int slots){
+    hb_prof *p = ctx->prof;
+    if (!p || !p->on) return;
+    const long long n = valid_iterations < p->marked ? valid_iterations : p->marked;
+    for (long long it = 0; it < n; it++)
+        for (int s = 0; s < slots && s < hb_prof::SLOTS; s++){
+            cudaEvent_t a = p->ev[it * (hb_prof::SLOTS + 1) + s], b = p->ev[it * (hb_prof::SLOTS + 1) + s + 1];
+            float ms = 0;
+            if (a && b && cudaEventElapsedTime(&ms, a, b) == cudaSuccess){ p->ms[s] += ms; p->n[s]++; }
+            else cudaGetLastError();
+        }
+    p->marked = 0;
+}
+
 extern "C" {
 
 const char* hb_version(void){ return "halab200 0.1 (sm_100a)"; }
@@ -131,8 +155,27 @@ int hb_ctx_destroy(hb_ctx *ctx){
     if (ctx->timer[0]) cudaEventDestroy(ctx->timer[0]);
     if (ctx->timer[1]) cudaEventDestroy(ctx->timer[1]);
     if (ctx->work) cudaFree(ctx->work);
+    if (ctx->prof){ for (cudaEvent_t e : ctx->prof->ev) if (e) cudaEventDestroy(e); delete ctx->prof; }
     cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->dscalars); cudaFreeHost(ctx->hscalars);
     delete ctx;
+    return HB_OK;
+}
+
+int hb_ctx_profile(hb_ctx *ctx, int enable){
+    HB_ARG(ctx, "ctx is null");
+    if (enable){
+        if (!ctx->prof) ctx->prof = new hb_prof();
+        for (int s = 0; s < hb_prof::SLOTS; s++){ ctx->prof->ms[s] = 0; ctx->prof->n[s] = 0; }
+        ctx->prof->marked = 0;
+    }
+    if (ctx->prof) ctx->prof->on = enable ? 1 : 0;
+    return HB_OK;
+}
+int hb_ctx_profile_read(const hb_ctx *ctx, int slot, double *ms_total, long long *launches){
+    HB_ARG(ctx && ms_total && launches, "null");
+    HB_ARG(slot >= 0 && slot < hb_prof::SLOTS, "slot");
+    *ms_total = ctx->prof ? ctx->prof->ms[slot] : 0.0;
+    *launches = ctx->prof ? ctx->prof->n[slot] : 0;
     return HB_OK;
 }
 

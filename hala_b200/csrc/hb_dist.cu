@@ -522,6 +522,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
         HB_LAUNCH_CHECK(ctx);
     });
 
+    hb_prof_begin(ctx);
     cudaEvent_t ev[2];
     HB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     HB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
@@ -540,6 +541,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
             HB_DISPATCH(dtype, {
                 cg_dstate<T> *st = (cg_dstate<T>*) state;
                 const bool vec = aligned16(x) && aligned16(r) && aligned16(Ap) && aligned16(p_old) && aligned16(p_new);
+                hb_prof_mark(ctx, it, 0);
                 if (fused){
                     ctx->peer_hook = pv; ctx->peer_epoch = g; ctx->peer_trot = trot; ctx->peer_twait = twait;
                     status = hb_spmv_dot_internal(ctx, A, p_old, Ap, &st->pAp_local, &st->done[parity]);
@@ -552,14 +554,17 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
                     peer_publish_kernel<T><<<1, 32, 0, ctx->stream>>>(pv, HB_PEER_CH_PAP, g, &st->pAp_local, &st->done[parity]);
                     ctx->launches++;
                 }
+                hb_prof_mark(ctx, it, 1);
                 if (vec) pcg_update_kernel<T, true><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, (const T*) Ap, (T*) r, ctx->partials, ctx->tickets + 6, pv);
                 else     pcg_update_kernel<T, false><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, (const T*) Ap, (T*) r, ctx->partials, ctx->tickets + 6, pv);
                 ctx->launches++;
+                hb_prof_mark(ctx, it, 2);
                 if (vec) pcg_direction_kernel<T, true><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
                                                                                              pv, d->send_idx, (cg_dhost*) hstat_dev);
                 else     pcg_direction_kernel<T, false><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
                                                                                               pv, d->send_idx, (cg_dhost*) hstat_dev);
                 ctx->launches++;
+                hb_prof_mark(ctx, it, 3);
             });
         }
         if (status != HB_OK) break;
@@ -580,6 +585,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
     int any_timeout = 0;
     if (status == HB_OK) status = peer_error_agree(d, &any_timeout);        // synchronises the stream
     else cudaStreamSynchronize(ctx->stream);
+    if (status == HB_OK) hb_prof_collect(ctx, (long long) hstat->iterations - 1, 3);
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     // HB_DEBUG_EPOCH_RULE=host: the round-1 rule (every host counts what it enqueued), kept as a test hook
     static const bool host_rule = [](){ const char *e = getenv("HB_DEBUG_EPOCH_RULE"); return e && e[0] == 'h'; }();
@@ -848,6 +854,7 @@ int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, 
     cudaEvent_t ev[2];
     HB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     HB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    hb_prof_begin(ctx);
     const int batch = 4;
     long long it = 0;
     int status = HB_OK;
@@ -858,14 +865,18 @@ int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, 
                 cg_dstate<T> *st = (cg_dstate<T>*) state;
                 // every rank runs the collectives of every enqueued iteration, converged or not (the kernels around them
                 // are skipped by the done flag); all ranks see the same flag, so the call sequences stay matched
+                hb_prof_mark(ctx, it, 0);
                 if ((status = hb_dist_halo_exchange(d, dtype, p)) != HB_OK) break;
                 if ((status = hb_spmv_dot_internal(ctx, A, p, Ap, &st->pAp, &st->done[parity])) != HB_OK) break;
+                hb_prof_mark(ctx, it, 1);
                 if ((status = hb_dist_allreduce_sum(d, dtype, &st->pAp, 1)) != HB_OK) break;
                 dcg_update_kernel<T><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, (const T*) p, (const T*) Ap, (T*) x, (T*) r, ctx->partials, ctx->tickets + 6);
                 ctx->launches++;
+                hb_prof_mark(ctx, it, 2);
                 if ((status = hb_dist_allreduce_sum(d, dtype, &st->rr, 1)) != HB_OK) break;
                 dcg_direction_kernel<T><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, (int) (it + 2), (const T*) r, (T*) p, (cg_dhost*) hstat_dev);
                 ctx->launches++;
+                hb_prof_mark(ctx, it, 3);
             });
         }
         if (status != HB_OK) break;
@@ -879,6 +890,7 @@ int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, 
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     if (status != HB_OK) return status;
     if (e != cudaSuccess) return hb_cuda_fail(e, "cudaStreamSynchronize");
+    hb_prof_collect(ctx, (long long) hstat->iterations - 1, 3);
     if (iters) *iters = hstat->iterations;
     if (res) *res = hstat->rnorm;
     return HB_OK;

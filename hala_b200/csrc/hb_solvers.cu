@@ -253,6 +253,7 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
     if ((rc = hb_spmv_internal(ctx, A, x, Ap, nullptr)) != HB_OK) return rc;                                  // p = A x  (cg:110)
     if ((rc = hb_cg_setup_internal(ctx, dtype, n, state, tol, max_iter, b, Ap, r, p, hstat_dev)) != HB_OK) return rc;
 
+    hb_prof_begin(ctx);
     event_pair evs;
     HB_CUDA(cudaEventCreateWithFlags(&evs.ev[0], cudaEventDisableTiming));
     HB_CUDA(cudaEventCreateWithFlags(&evs.ev[1], cudaEventDisableTiming));
@@ -261,11 +262,15 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
     for (long long bidx = 0; ; bidx++){
         for (int j = 0; j < batch; j++, it++){
             const int parity = (int) (it & 1);
+            hb_prof_mark(ctx, it, 0);
             if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;               // Ap = A p ; <p,Ap>
+            hb_prof_mark(ctx, it, 1);
             if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev, 0)) != HB_OK) return rc;
+            hb_prof_mark(ctx, it, 2);
             // iteration `it` turns the operator-application counter into it + 2 (setup leaves it at 1)
             const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
             if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, it_now, r, p, x)) != HB_OK) return rc;
+            hb_prof_mark(ctx, it, 3);
         }
         HB_CUDA(cudaEventRecord(evs.ev[bidx & 1], ctx->stream));
         if (bidx > 0){
@@ -274,6 +279,7 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
         }
     }
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    hb_prof_collect(ctx, (long long) hstat->iterations - 1, 3);
     if (iters) *iters = hstat->iterations;
     if (res) *res = hstat->rnorm;
     return HB_OK;
@@ -309,6 +315,7 @@ int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int
     if ((rc = precon(r, z)) != HB_OK) return rc;                                                              // z = P^-1 r            (cg:116)
     if ((rc = hb_pcg_dot_internal(ctx, dtype, n, state, 0, r, z, p)) != HB_OK) return rc;                     // p = z ; zr = <r,z>    (cg:121-123)
 
+    hb_prof_begin(ctx);
     constexpr int lag = 2, nev = 4;
     cudaEvent_t ev[nev];
     for (int k = 0; k < nev; k++) ev[k] = nullptr;
@@ -316,12 +323,17 @@ int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int
     for (int k = 0; k < nev; k++) HB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
     for (long long it = 0; ; it++){
         const int parity = (int) (it & 1);
+        hb_prof_mark(ctx, it, 0);
         if ((rc = hb_spmv_dot_internal(ctx, A, p, Ap, pap, done_flag)) != HB_OK) return rc;                   // Ap = A p ; <p,Ap>
+        hb_prof_mark(ctx, it, 1);
         if ((rc = hb_cg_update_internal(ctx, dtype, n, state, parity, Ap, r, hstat_dev, 1)) != HB_OK) return rc;
+        hb_prof_mark(ctx, it, 2);
         if ((rc = precon(r, z)) != HB_OK) return rc;
         if ((rc = hb_pcg_dot_internal(ctx, dtype, n, state, parity ^ 1, r, z, nullptr)) != HB_OK) return rc;  // new <r,z>
+        hb_prof_mark(ctx, it, 3);
         const int it_now = (int) (it + 2 < 0x7fffffffLL ? it + 2 : 0x7fffffffLL);
         if ((rc = hb_cg_direction_internal(ctx, dtype, n, state, parity, it_now, z, p, x)) != HB_OK) return rc;
+        hb_prof_mark(ctx, it, 4);
         HB_CUDA(cudaEventRecord(ev[it % nev], ctx->stream));
         if (hstat->done) break;                                                                               // a glance at the mapped status: no stall
         if (it >= lag){
@@ -330,6 +342,7 @@ int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int
         }
     }
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    hb_prof_collect(ctx, (long long) hstat->iterations - 1, 4);     // slot 2 = the caller's preconditioner + <r,z>
     if (iters) *iters = hstat->iterations;
     if (res) *res = hstat->rnorm;
     return HB_OK;

@@ -183,6 +183,15 @@ def cg_iter_bytes(N, nnz, itemsize):
     return nnz * (itemsize + 4) + (N + 1) * 4 + 11 * N * itemsize
 
 
+def gmres_iter_bytes(N, nnz, itemsize, restart):
+    """Algorithmic bytes of one GMRES(m) inner iteration averaged over a restart cycle (basis size k = 1..m): SpMV, multi-dot
+    (k columns + the vector once per chunk of 16 columns), multi-axpy + norm (k columns, r read and written), normalise-and-append
+    (read r, write the new column): DESIGN.md §4."""
+    ks = range(1, restart + 1)
+    per_k = [(k + (k + 15) // 16) + (k + 2) + 2 for k in ks]
+    return spmv_bytes(N, nnz, itemsize) + int(sum(per_k) / len(per_k) * N * itemsize)
+
+
 # ---------------------------------------------------------------- triangular / ILU test inputs (SURVEY.md §8 row f1)
 F1_CASES = (("lap3d27", 6), ("convdiff7", 7), ("lap2d", 13))      # (generator, size) of the recorded trsv / ILU parity cases
 

@@ -51,6 +51,12 @@ int hb_ctx_sync(hb_ctx *ctx);                                   /* gpu_engine::s
 int hb_ctx_set_pointer_mode(hb_ctx *ctx, int mode);             /* set/reset_blas_device_pntr (:105-111) */
 int hb_ctx_get_pointer_mode(const hb_ctx *ctx, int *mode);      /* get_blas_pointer_mode (:112-117) */
 int hb_ctx_launch_count(const hb_ctx *ctx, long long *count);   /* kernels launched through this context so far */
+/* per-kernel timing of the solver loops: while enabled, hb_cg / hb_pcg / hb_dist_cg bracket every launch of the first 512 iterations with
+ * CUDA events on the context's stream; read = total milliseconds and number of launches of kernel `slot` of the iteration (CG: 0 SpMV
+ * fused with <p,Ap>, 1 residual update + norm, 2 solution + direction update [hb_pcg: 2 <r,z>, 3 direction]) since it was enabled.
+ * Costs four event records per iteration; off by default. */
+int hb_ctx_profile(hb_ctx *ctx, int enable);
+int hb_ctx_profile_read(const hb_ctx *ctx, int slot, double *ms_total, long long *launches);
 int hb_ctx_trim(hb_ctx *ctx);                                   /* frees the cached solver workspace (kept across hb_cg / hb_gmres calls) */
 
 /* ---- device timers (CUDA events on the context stream) — measurement plumbing for bench.py; the reference only has the

@@ -77,6 +77,18 @@ class _Lib:
         assert rc == 0, rc
         return x, it.value
 
+    def gen_stencil7(self, n, lower=-1.0, diag=6.0, upper=-1.0, row_lo=0, row_hi=None):
+        """rows [row_lo, row_hi) of the n^3 7-point stencil, generated in C (oracle only): (pntr, indx, vals)"""
+        f = getattr(self.lib, self.prefix + "gen_stencil7")
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        row_hi = n ** 3 if row_hi is None else row_hi
+        nnz = f(n, row_lo, row_hi, lower, diag, upper, None, None, None)
+        pntr = np.empty(row_hi - row_lo + 1, dtype=np.int32)
+        indx, vals = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.float64)
+        f(n, row_lo, row_hi, lower, diag, upper, _ptr(pntr), _ptr(indx), _ptr(vals))
+        return pntr, indx, vals
+
     def blas1(self, op, x, y=None, alpha=1.0, n=None, incx=1, incy=1):
         dt = x.dtype
         code = CODE[dt]
@@ -201,3 +213,50 @@ def reference(cpatch=False):
         except OSError:
             _cache[key] = None
     return _cache[key]
+
+
+class _RefGpu:
+    """The unmodified reference's own gpu_engine path (cuSPARSE + cuBLAS, oracle/_ref/libhala_ref_gpu.so): bench.py's
+    gpu_reference leg.  All arrays are device pointers (ints)."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.lib.refgpu_version.restype = C.c_char_p
+        self.lib.refgpu_last_error.restype = C.c_char_p
+        self.version = self.lib.refgpu_version().decode()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.refgpu_last_error().decode()}")
+
+    def spmv_us(self, code, rows, cols, nnz, pntr, indx, vals, x, y, warmup=5, reps=50):
+        us = C.c_double(0)
+        vp = C.c_void_p
+        self._check(self.lib.refgpu_spmv(code, rows, cols, nnz, vp(pntr), vp(indx), vp(vals), vp(x), vp(y), warmup, reps, C.byref(us)), "refgpu_spmv")
+        return us.value
+
+    def cg(self, code, rows, nnz, pntr, indx, vals, b, x, tol, max_iter):
+        it, sec = C.c_int(0), C.c_double(0)
+        vp = C.c_void_p
+        self._check(self.lib.refgpu_cg(code, rows, nnz, vp(pntr), vp(indx), vp(vals), vp(b), vp(x), C.c_double(tol), int(max_iter),
+                                       C.byref(it), C.byref(sec)), "refgpu_cg")
+        return it.value, sec.value
+
+    def gmres(self, code, rows, nnz, pntr, indx, vals, b, x, tol, max_outer, restart):
+        it, sec = C.c_int(0), C.c_double(0)
+        vp = C.c_void_p
+        self._check(self.lib.refgpu_gmres(code, rows, nnz, vp(pntr), vp(indx), vp(vals), vp(b), vp(x), C.c_double(tol), int(max_outer), int(restart),
+                                          C.byref(it), C.byref(sec)), "refgpu_gmres")
+        return it.value, sec.value
+
+
+def reference_gpu():
+    """The reference's cuSPARSE/cuBLAS path, or None when it was never built or its CUDA libraries do not load here."""
+    if "refgpu" not in _cache:
+        path = os.path.join(HERE, "_ref", "libhala_ref_gpu.so")
+        try:
+            _preload_blas_deps()
+            _cache["refgpu"] = _RefGpu(path) if os.path.exists(path) else None
+        except OSError:
+            _cache["refgpu"] = None
+    return _cache["refgpu"]

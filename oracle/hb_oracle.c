@@ -200,3 +200,26 @@ int orc_spmm(int dtype, char transa, char transb, int M, int N, int K, const voi
 }
 
 const char* orc_version(void){ return "hala_b200 CPU oracle (restatement of LIBHALA/hala 1.1.0 cpu_engine path)"; }
+
+/* Host generator of the bench matrix for the reference arm of bench.py (the numpy generator hala_b200/matgen._stencil needs minutes
+ * and ~40 GB at 512^3): rows [row_lo, row_hi) of the n^3 7-point stencil with lexicographic index (k*n + j)*n + i, Dirichlet
+ * truncation, lower neighbours `lower`, diagonal `diag`, upper neighbours `upper` (Laplacian: -1, 6, -1; convection-diffusion:
+ * -1-d, 6, -1+d).  Bit-identical to matgen.lap3d7 / convdiff7 (tests/test_oracle.py).  pntr has row_hi - row_lo + 1 entries and
+ * starts at 0; returns the number of non-zeros written (call with indx == NULL to size the arrays). */
+long long orc_gen_stencil7(int n, long long row_lo, long long row_hi, double lower, double diag, double upper, int *pntr, int *indx, double *vals){
+    const long long n2 = (long long) n * n;
+    long long nz = 0;
+    if (pntr) pntr[0] = 0;
+    for (long long row = row_lo; row < row_hi; row++){
+        const int i = (int) (row % n), j = (int) ((row / n) % n), k = (int) (row / n2);
+        const long long col[7] = {row - n2, row - n, row - 1, row, row + 1, row + n, row + n2};
+        const int ok[7] = {k > 0, j > 0, i > 0, 1, i < n - 1, j < n - 1, k < n - 1};
+        const double v[7] = {lower, lower, lower, diag, upper, upper, upper};
+        for (int s = 0; s < 7; s++) if (ok[s]){
+            if (indx){ indx[nz] = (int) col[s]; vals[nz] = v[s]; }
+            nz++;
+        }
+        if (pntr) pntr[row - row_lo + 1] = (int) nz;
+    }
+    return nz;
+}

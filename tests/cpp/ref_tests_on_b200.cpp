@@ -85,6 +85,107 @@ template<typename T> void solvers_on_engines(){
 }
 
 
+// The fused iteration behind the UNCHANGED template calls (hala_b200/gpu/hala_gpu_solvers.hpp): what a HALA user gets by swapping the
+// include path.  Counts the library's kernel launches per iteration (hb_ctx_launch_count), compares iteration counts with the same
+// call on cpu_engine, and pins the corner cases of the preconditioner bridge.
+template<typename T> void fused_front_doors(){
+    current_test<T> tests("fused solve_cg/gmres");
+    using P = typename hala::define_standard_precision<T>::value_type;
+    const int n = 40, N = n * n;
+    const P tol = std::is_same<P, float>::value ? 1.E-4f : 1.E-9;
+    std::vector<int> pntr, indx; std::vector<T> vals;
+    lap2d<T>(n, pntr, indx, vals);
+    std::vector<T> b(N, hala::get_cast<T>(1.0 / n));
+    hala::cpu_engine ecpu;
+    hala::gpu_engine egpu(0);
+    auto gp = egpu.load(pntr); auto gi = egpu.load(indx); auto gv = egpu.load(vals); auto gb = egpu.load(b);
+    auto launches = [&]()->long long{ long long c = 0; hb_ctx_launch_count(egpu, &c); return c; };
+    const hala::stop_criteria<P> stop(tol, 1000);
+
+    // 1. identity preconditioner written as the reference's tests write it (a copy): 4 library launches + the copy per iteration
+    std::vector<T> xcpu, x1, x2, x3, x4;
+    int it_cpu = hala::solve_cg(ecpu, stop, pntr, indx, vals, [&](auto const &in, auto &out)->void{ hala::vcopy(ecpu, in, out); }, b, xcpu);
+    hala::gpu_vector<T> gx(egpu.device());
+    long long l0 = launches();
+    int it1 = hala::solve_cg(egpu, stop, gp, gi, gv, [&](auto const &in, auto &out)->void{ hala::vcopy(egpu, in, out); }, gb, gx);
+    long long per_it = (launches() - l0) / it1;
+    gx.unload(x1);
+    hassert(std::abs(it1 - it_cpu) <= 2);
+    hassert(per_it <= 5);                                           // spmv+dot, update, [copy], dot, direction (+ a few skipped past the stop)
+    hassert(testvec(x1, xcpu, 1.E+6 * hala::norm2(xcpu)));
+
+    // 2. hala::identity_preconditioner: the unpreconditioned fused iteration, 3 launches
+    hala::gpu_vector<T> gx2(egpu.device());
+    l0 = launches();
+    int it2 = hala::solve_cg(egpu, stop, gp, gi, gv, hala::identity_preconditioner(), gb, gx2);
+    per_it = (launches() - l0) / it2;
+    gx2.unload(x2);
+    hassert(std::abs(it2 - it_cpu) <= 2);
+    hassert(per_it <= 3);
+    hassert(testvec(x2, xcpu, 1.E+6 * hala::norm2(xcpu)));
+
+    // 3. a real preconditioner: Jacobi on a matrix with a varying diagonal (element-wise divide = tbsv with bandwidth 0 on the GPU)
+    std::vector<T> dvals = vals, diag(N);
+    for(int i=0; i<N; i++) for(int j=pntr[i]; j<pntr[i+1]; j++) if (indx[j] == i){ dvals[j] = hala::get_cast<T>(4.0 + (i % 7) * 0.5); diag[i] = dvals[j]; }
+    auto gdv = egpu.load(dvals); auto gdiag = egpu.load(diag);
+    std::vector<T> xjc;
+    int jc = hala::solve_cg(ecpu, stop, pntr, indx, dvals,
+                            [&](auto const &in, auto &out)->void{ hala::vcopy(ecpu, in, out); for(int i=0; i<N; i++) out[i] /= diag[i]; }, b, xjc);
+    hala::gpu_vector<T> gx3(egpu.device());
+    int jg = hala::solve_cg(egpu, stop, gp, gi, gdv,
+                            [&](auto const &in, auto &out)->void{ hala::vcopy(egpu, in, out); hala::tbsv(egpu, 'U', 'N', 'N', N, 0, gdiag, out); }, gb, gx3);
+    gx3.unload(x3);
+    hassert(std::abs(jc - jg) <= 2);
+    hassert(jg < it_cpu + 10);
+    hassert(testvec(x3, xjc, 1.E+6 * hala::norm2(xjc)));
+
+    // 4. a preconditioner that hands back storage of its own (move-assignment into the output) and one that throws
+    hala::gpu_vector<T> gx4(egpu.device());
+    int it4 = hala::solve_cg(egpu, stop, gp, gi, gv, [&](auto const &in, auto &out)->void{ out = egpu.vcopy(in); }, gb, gx4);
+    gx4.unload(x4);
+    hassert(std::abs(it4 - it_cpu) <= 2);
+    hassert(testvec(x4, xcpu, 1.E+6 * hala::norm2(xcpu)));
+    bool thrown = false;
+    try{
+        hala::gpu_vector<T> gx5(egpu.device());
+        hala::solve_cg(egpu, stop, gp, gi, gv, [&](auto const&, auto&)->void{ throw std::runtime_error("precon says no"); }, gb, gx5);
+    }catch(std::runtime_error &e){ thrown = (std::string(e.what()) == "precon says no"); }
+    hassert(thrown);
+
+    // 5. ILU-preconditioned CG through solve_cg_ilu(gpu_engine, ...) with a ready factor and on the fly, against cpu_engine
+    std::vector<T> xic, xig;
+    int ic = hala::solve_cg_ilu(ecpu, stop, pntr, indx, vals, b, xic);
+    auto ilu = hala::make_ilu(egpu, gp, gi, gv, 'N');
+    hala::gpu_vector<T> gxi(egpu.device());
+    int ig = hala::solve_cg_ilu(egpu, stop, gp, gi, gv, ilu, gb, gxi);
+    gxi.unload(xig);
+    hassert(std::abs(ic - ig) <= 2);
+    hassert(testvec(xig, xic, 1.E+6 * hala::norm2(xic)));
+    hala::gpu_vector<T> gxf(egpu.device());
+    int ig2 = hala::solve_cg_ilu(egpu, stop, gp, gi, gv, gb, gxf);
+    hassert(ig2 == ig);
+
+    // 6. GMRES: copy-lambda, identity tag and ILU (solve_gmres_ilu is the reference's own template: it must land on the fused overload)
+    for(int i=0; i<N; i++) for(int j=pntr[i]; j<pntr[i+1]; j++) if (indx[j] < i) vals[j] = hala::get_cast<T>(-1.5); else if (indx[j] > i) vals[j] = hala::get_cast<T>(-0.5);
+    gv.load(vals);
+    const hala::stop_criteria<P> gstop(tol, 100);
+    std::vector<T> ycpu, y1, y2, yic, yig;
+    int g_cpu = hala::solve_gmres(ecpu, gstop, 20, pntr, indx, vals, [&](auto const &in, auto &out)->void{ hala::vcopy(ecpu, in, out); }, b, ycpu);
+    hala::gpu_vector<T> gy1(egpu.device()), gy2(egpu.device()), gy3(egpu.device());
+    int g1 = hala::solve_gmres(egpu, gstop, 20, gp, gi, gv, [&](auto const &in, auto &out)->void{ hala::vcopy(egpu, in, out); }, gb, gy1);
+    int g2 = hala::solve_gmres(egpu, gstop, 20, gp, gi, gv, hala::identity_preconditioner(), gb, gy2);
+    gy1.unload(y1); gy2.unload(y2);
+    hassert(std::abs(g1 - g_cpu) <= 2);
+    hassert(g2 == g1);
+    hassert(testvec(y1, ycpu, 1.E+6 * hala::norm2(ycpu)));
+    hassert(testvec(y2, ycpu, 1.E+6 * hala::norm2(ycpu)));
+    int gic = hala::solve_gmres_ilu(ecpu, gstop, 20, pntr, indx, vals, b, yic);
+    int gig = hala::solve_gmres_ilu(egpu, gstop, 20, gp, gi, gv, gb, gy3);
+    gy3.unload(yig);
+    hassert(std::abs(gic - gig) <= 2);
+    hassert(testvec(yig, yic, 1.E+6 * hala::norm2(yic)));
+}
+
 // Row f3 through the header layer: a gpu_sparse_matrix kept across products, op 'T' / 'C' on the cached transpose in its three modes,
 // values rewritten in place between products (the view is non-owning, reference gpu/hala_cuda_sparse_general.hpp:186-190), against
 // hala::sparse_gemv on the CPU engine.
@@ -178,6 +279,7 @@ int main(int argc, char**){
 
     begin_report(std::string("reference solver templates on gpu_engine / mixed_engine"));
     perform([]()->void{ solvers_on_engines<float>(); solvers_on_engines<double>(); solvers_on_engines<std::complex<float>>(); solvers_on_engines<std::complex<double>>(); });
+    perform([]()->void{ fused_front_doors<float>(); fused_front_doors<double>(); fused_front_doors<std::complex<float>>(); fused_front_doors<std::complex<double>>(); });
 
     end_report(name);
     return test_result();

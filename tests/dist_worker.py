@@ -30,8 +30,11 @@ def check_sequence_numbers(comm, dist, torch, dev, world, final=False):
         dist.all_gather(lst, t)
         assert all(torch.equal(q, t) for q in lst), ("sequence numbers differ between ranks", [q.tolist() for q in lst])
     if final:
-        _expect("HB_EXPECT_FALLBACKS", info["peer_fallbacks"])
-        _expect("HB_EXPECT_REPAIRS", info["epoch_repairs"])
+        # a repair is counted by the ranks that were behind, a fall-back by every rank: look at the totals over ranks
+        t = torch.tensor([info["peer_fallbacks"], info["epoch_repairs"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        _expect("HB_EXPECT_FALLBACKS", int(t[0].item()))
+        _expect("HB_EXPECT_REPAIRS", int(t[1].item()))
 
 
 def main():
@@ -80,11 +83,14 @@ def main():
         if want:
             assert comm.transport() == want, (comm.transport(), want)
         check_sequence_numbers(comm, dist, torch, dev, world)
-        # --- the same SpMV again now that the transport of this plan is up (peer runs: halo pushed into the neighbours' exchange buffers)
-        x_ext[n_owned:] = 0
-        y.zero_()
-        comm.spmv(prob["A"], C.c_void_p(x_ext.data_ptr()), C.c_void_p(y.data_ptr()))
-        assert np.max(np.abs(y.cpu().numpy() - yref)) <= 1e-13 * scale, (name, rank, "spmv after cg")
+        # --- the same SpMV again now that the transport of this plan is up (peer runs: halo pushed into the neighbours' exchange buffers).
+        # Not under the round-1 counting rule (test hook): a stand-alone exchange relies on the sequence numbers being equal after
+        # every solve, which is exactly what that rule breaks; solves re-base them, a single exchange does not.
+        if os.environ.get("HB_DEBUG_EPOCH_RULE") != "host":
+            x_ext[n_owned:] = 0
+            y.zero_()
+            comm.spmv(prob["A"], C.c_void_p(x_ext.data_ptr()), C.c_void_p(y.data_ptr()))
+            assert np.max(np.abs(y.cpu().numpy() - yref)) <= 1e-13 * scale, (name, rank, "spmv after cg")
         # --- a second solve from a non-zero initial guess (x0 halo over NCCL, epochs continue): converges in <= the first count
         x.copy_(torch.from_numpy(xo[lo:hi]).to(dev) * 0.5)
         it3, res3 = comm.cg(prob["A"], C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), tol, 10 ** 6)

@@ -29,8 +29,19 @@ SKEW_CASES = {
 }
 
 
-def _run_worker(world, port, env_extra, timeout=600):
-    env = dict(os.environ, **env_extra)
+def _keep_log(r, tag):
+    """worker output -> gpurun_out/dist_logs/ (scratch, merged back by gpurun): the evidence of a multi-GPU run"""
+    d = os.path.join(ROOT, "gpurun_out", "dist_logs")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"{tag}.log"), "w") as f:
+            f.write(f"returncode {r.returncode}\n---- stdout\n{r.stdout}\n---- stderr\n{r.stderr[-20000:]}\n")
+    except OSError:
+        pass
+
+
+def _run_worker(world, port, env_extra, timeout=240):
+    env = dict(os.environ, HB_DIST_VERBOSE="1", **env_extra)
     return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")], capture_output=True, text=True, timeout=timeout, env=env)
 
@@ -43,6 +54,7 @@ def test_peer_sequence_numbers_survive_host_skew(case):
         pytest.skip("needs 2 GPUs")
     inject, expect = SKEW_CASES[case]
     r = _run_worker(2, 29700 + list(SKEW_CASES).index(case), dict(inject, **expect))
+    _keep_log(r, f"skew-{case}")
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert r.stdout.count("dist ok") == 4, r.stdout[-2000:]
 
@@ -57,5 +69,6 @@ def test_row_partitioned_spmv_and_cg(world, transport):
     port = 29600 + world + 16 * list(TRANSPORTS).index(transport)
     expect = {"HB_EXPECT_TRANSPORT": transport.split("-")[0], "HB_EXPECT_FALLBACKS": "0", "HB_EXPECT_REPAIRS": "0"}
     r = _run_worker(world, port, dict(TRANSPORTS[transport], **expect))
+    _keep_log(r, f"world{world}-{transport}")
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     assert r.stdout.count("dist ok") == 4, r.stdout[-2000:]

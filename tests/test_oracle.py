@@ -246,3 +246,14 @@ def test_oracle_spmm_matches_recorded_reference(orc, golden_f2, dt):
             got = orc.spmm(ta, tb, n, N, n, p, i, v, B, ldb, alpha=1.5, beta=0.5, C=C0, ldc=n + 1)
             want = golden_f2[f"spmm/convdiff7:7/{dt}/{ta}{tb}"]
             assert np.abs(got - want).max() <= F1_TOL[dt] * np.abs(want).max(), (ta, tb)
+
+
+def test_c_stencil_generator_equals_matgen(orc):
+    """bench.py's reference arm builds the 512^3 matrix with the oracle's C generator: bit-identical to hala_b200.matgen."""
+    for n in (3, 7, 12):
+        N = n ** 3
+        for args, gen in (((-1.0, 6.0, -1.0), mg.lap3d7), ((-1.5, 6.0, -0.5), mg.convdiff7)):
+            for lo, hi in ((0, N), (n * n, N - 5)):
+                a = orc.gen_stencil7(n, *args, row_lo=lo, row_hi=hi)
+                b = gen(n, row_lo=lo, row_hi=hi)
+                assert all(np.array_equal(u, v) and u.dtype == v.dtype for u, v in zip(a, b)), (n, lo, hi)
