@@ -57,6 +57,16 @@ static constexpr size_t HB_SCALAR_BYTES  = 4096;
 static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids never exceed this
 
 struct hb_tcache;                       // cached transposed copy behind op 'T' / 'C' (hb_transpose.cu)
+// heavy-tailed row lengths: virtual-row view + tile table of the streaming kernel (hb_spmv_pipe.cuh, VS form); all arrays on the device
+struct hb_vsplit {
+    int nvrows = 0, ntiles = 0, nsplit = 0, nparts = 0, seg = 0, tpr = 2, grid = 0;
+    int *vpntr = nullptr;               // nvrows + 1: row pointers of the virtual rows (into the caller's indx / vals)
+    int *vmap = nullptr;                // nvrows: >= 0 the real row this virtual row IS; < 0: ~index of its slot in `part`
+    int *trow = nullptr, *tnz = nullptr;// ntiles + 1: first virtual row / first non-zero of tile t
+    int *srow = nullptr, *spart = nullptr;  // nsplit: the split rows; nsplit + 1: first slot of each in `part`
+    void *part = nullptr;               // nparts partial sums (scalars of the matrix type)
+    int *cta_tiles = nullptr;           // grid + 1: contiguous equal-nnz pieces of the tile list
+};
 struct hb_csr {
     hb_ctx *ctx = nullptr;
     int dtype = HB_F64;
@@ -75,6 +85,7 @@ struct hb_csr {
     int  pipe_cfg = 0;                  // which (THREADS, CH, STAGES) instantiation; HB_PIPE_CFG overrides for probing
     int  tpr = 1;                       // lanes per row of the streaming kernel: from the mean row length, one notch up for heavy-tailed rows
     hb_tcache *tc = nullptr;            // transpose mode + (lazily built) CSR of A^T; owned
+    hb_vsplit *vs = nullptr;            // heavy-tailed matrices only (hb_csr_create); owned
     // row-partitioned runs (local matrix = [owned | ghost] columns, ghosts = columns >= rows): rotation of the streaming kernel's
     // tile sweep that puts the tiles touching ghost columns last, and the first position of the rotated order that touches one
     // (hb_csr_halo_order, computed once on first use)

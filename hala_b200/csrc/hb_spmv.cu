@@ -314,7 +314,7 @@ static int launch_pipe_cfg(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scala
                                                             (TPR <= 2 && A->rows == A->cols) ? 2 : 0, A->cols,
                                                             DOT ? (const peer_view*) ctx->peer_hook : nullptr, ctx->peer_epoch, (size_t) 0, (size_t) 0, (size_t) 0,
                                                             (DOT && ctx->peer_hook && !A->pipe_contiguous) ? ctx->peer_trot : 0,
-                                                            (DOT && ctx->peer_hook && !A->pipe_contiguous) ? ctx->peer_twait : 0);
+                                                            (DOT && ctx->peer_hook && !A->pipe_contiguous) ? ctx->peer_twait : 0, vsplit_view());
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -343,7 +343,7 @@ static int launch_pipe_mm_cfg(hb_ctx *ctx, const hb_csr *A, const T *Bt, size_t 
     scalar_arg<T> one; one.value = one_of<T>(); one.dev = nullptr;
     scalar_arg<T> zero; zero.value = zero_of<T>(); zero.dev = nullptr;
     k<<<A->pipe_grid[CFG], C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, Bt, Ct, one, zero,
-                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct, (size_t) 0, 0, 0);
+                                                            nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, 0, A->cols, nullptr, 0ull, ldbt, ldct, (size_t) 0, 0, 0, vsplit_view());
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -380,7 +380,7 @@ static int launch_pipe_lpc_cfg(hb_ctx *ctx, const hb_csr *A, int nb, const T *B,
     const long long ntiles = ((long long) A->rows + tile_rows - 1) / tile_rows;
     const int grid = (int) std::min<long long>(ntiles, (long long) ctx->num_sms * occ);
     k<<<grid, C::THREADS, smem, ctx->stream>>>(A->rows, A->nnz, A->pntr, A->indx, (const T*) A->vals, B, Cm, alpha, beta,
-                                               nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, nb, A->cols, nullptr, 0ull, sxr, ldc, sxc, 0, 0);
+                                               nullptr, ctx->partials, ctx->tickets + 1, nullptr, nullptr, nb, A->cols, nullptr, 0ull, sxr, ldc, sxc, 0, 0, vsplit_view());
     HB_LAUNCH_CHECK(ctx);
     return HB_OK;
 }
@@ -431,6 +431,140 @@ int hb_spmm_interleaved(hb_ctx *ctx, const hb_csr *A, int nbp, const void *Bt, s
     return HB_OK;
 }
 
+// ---- heavy-tailed row lengths: virtual-row / tile-table form of the streaming kernel (spmv_pipe_kernel<..., VS = true>)
+static constexpr int VS_THREADS = pipe_cfg<0>::THREADS, VS_STAGES = pipe_cfg<0>::STAGES;
+static void vsplit_free(hb_vsplit *v){
+    if (!v) return;
+    for (void *p : {(void*) v->vpntr, (void*) v->vmap, (void*) v->trow, (void*) v->tnz, (void*) v->srow, (void*) v->spart, v->part, (void*) v->cta_tiles})
+        if (p) cudaFree(p);
+    delete v;
+}
+template<typename T, int TPR, bool DOT>
+static int vsplit_occupancy(){
+    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, VS_THREADS, TPR, VS_STAGES, DOT, 0, false, true>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, VS_THREADS, smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    return n;
+}
+static int vsplit_occupancy_any(int dtype, int tpr){
+    HB_DISPATCH(dtype, {
+        int a = 0, b = 0;
+        switch (tpr){
+            case 8:  a = vsplit_occupancy<T, 8, false>(); b = vsplit_occupancy<T, 8, true>(); break;
+            case 4:  a = vsplit_occupancy<T, 4, false>(); b = vsplit_occupancy<T, 4, true>(); break;
+            default: a = vsplit_occupancy<T, 2, false>(); b = vsplit_occupancy<T, 2, true>(); break;
+        }
+        return a < b ? a : b;
+    });
+    return 0;
+}
+template<typename T, int TPR, bool DOT>
+static int launch_pipe_vs_tpr(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    const hb_vsplit *v = A->vs;
+    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T));
+    auto k = spmv_pipe_kernel<T, VS_THREADS, TPR, VS_STAGES, DOT, 0, false, true>;
+    vsplit_view view;
+    view.trow = v->trow; view.tnz = v->tnz; view.vmap = v->vmap; view.part = v->part; view.ntiles = v->ntiles;
+    k<<<v->grid, VS_THREADS, smem, ctx->stream>>>(v->nvrows, A->nnz, v->vpntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
+                                                  A->pipe_contiguous ? v->cta_tiles : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip, 0, A->cols,
+                                                  nullptr, 0ull, (size_t) 0, (size_t) 0, (size_t) 0, 0, 0, view);
+    HB_LAUNCH_CHECK(ctx);
+    if (v->nsplit > 0){
+        const int grid = std::min((v->nsplit + 7) / 8, ctx->num_sms * 4);
+        vsplit_combine_kernel<T, DOT><<<grid, 256, 0, ctx->stream>>>(v->nsplit, v->srow, v->spart, (const T*) v->part, alpha, beta, y, x,
+                                                                    ctx->partials, ctx->tickets + 7, dot_out, skip);
+        HB_LAUNCH_CHECK(ctx);
+    }
+    return HB_OK;
+}
+template<typename T, bool DOT>
+static int launch_pipe_vs(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
+    switch (A->vs->tpr){
+        case 8:  return launch_pipe_vs_tpr<T, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        case 4:  return launch_pipe_vs_tpr<T, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        default: return launch_pipe_vs_tpr<T, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+    }
+}
+// One-time analysis on the host (heavy-tailed matrices only: one 4(rows+1)-byte read-back, two linear host loops, ~35 MB of tables for the
+// 2^22-row power-law matrix): segments of at most SEG = (CAP - 8) / 4 entries, so that ANY four consecutive virtual rows fit a ring stage
+// and tiles can start at multiples of four virtual rows (16-byte aligned slices of vpntr for the bulk copies).
+static int vsplit_build(hb_ctx *ctx, hb_csr *A){
+    const size_t es = hb_dtype_size(A->dtype);
+    const int cap = VS_THREADS * (es == 16 ? 4 : 8);
+    int tpr = A->tpr < 2 ? 2 : (A->tpr > 8 ? 8 : A->tpr);
+    const int occ = vsplit_occupancy_any(A->dtype, tpr);
+    if (occ < 1) return HB_OK;                                  // cannot run here: the matrix keeps the general kernel
+    const int tile_rows = VS_THREADS / tpr, seg = ((cap - 8) / 4) & ~3;
+    const int rows = A->rows;
+    std::vector<int> hp((size_t) rows + 1);
+    HB_CUDA(cudaMemcpyAsync(hp.data(), A->pntr, sizeof(int) * hp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> vpntr, vmap, srow, spart(1, 0);
+    vpntr.reserve((size_t) rows + rows / 8 + 8); vmap.reserve((size_t) rows + rows / 8 + 8);
+    vpntr.push_back(hp[0]);
+    int nparts = 0;
+    for (int r = 0; r < rows; r++){
+        const int b = hp[(size_t) r], e = hp[(size_t) r + 1], len = e - b;
+        if (len <= seg){ vpntr.push_back(e); vmap.push_back(r); continue; }
+        const int nseg = (len + seg - 1) / seg;
+        const int sl = (((len + nseg - 1) / nseg) + 3) & ~3;   // equal segments, a multiple of 4 entries each (<= seg since seg % 4 == 0)
+        for (int q = 0; q < nseg; q++){
+            const long long end = (long long) b + (long long) (q + 1) * sl;
+            vpntr.push_back((int) (end < e ? end : e));
+            vmap.push_back(~nparts);
+            nparts++;
+        }
+        srow.push_back(r); spart.push_back(nparts);
+    }
+    const int nv = (int) vmap.size();
+    std::vector<int> trow, tnz;
+    for (int t0 = 0; t0 < nv; ){
+        const int a0 = vpntr[(size_t) t0] & ~3;
+        int r = t0;
+        while (r < nv && r - t0 < tile_rows){
+            const int r4 = std::min(r + 4, nv);
+            if (vpntr[(size_t) r4] - a0 > cap) break;
+            r = r4;
+        }
+        if (r == t0){ hb_set_error("internal: a group of four virtual rows exceeds a ring stage"); return HB_ERR_ARG; }
+        trow.push_back(t0);
+        t0 = r;
+    }
+    trow.push_back(nv);
+    const int nt = (int) trow.size() - 1;
+    tnz.resize(trow.size());
+    for (size_t t = 0; t < trow.size(); t++) tnz[t] = vpntr[(size_t) trow[t]];
+    int G = ctx->num_sms * occ;
+    if (G > nt) G = nt;
+    std::vector<int> cta((size_t) G + 1);
+    for (int g = 0; g <= G; g++){
+        const long long target = (long long) hp[0] + ((long long) A->nnz * g) / G;
+        cta[(size_t) g] = g == G ? nt : (int) (std::lower_bound(tnz.begin(), tnz.begin() + nt, (int) target) - tnz.begin());
+    }
+    hb_vsplit *v = new hb_vsplit();
+    v->nvrows = nv; v->ntiles = nt; v->nsplit = (int) srow.size(); v->nparts = nparts; v->seg = seg; v->tpr = tpr; v->grid = G;
+    auto up = [&](int **dst, const std::vector<int> &src)->cudaError_t{
+        cudaError_t e = cudaMalloc((void**) dst, sizeof(int) * std::max<size_t>(src.size(), 4));
+        if (e == cudaSuccess && !src.empty()) e = cudaMemcpyAsync(*dst, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice, ctx->stream);
+        return e;
+    };
+    cudaError_t e = up(&v->vpntr, vpntr);
+    if (e == cudaSuccess) e = up(&v->vmap, vmap);
+    if (e == cudaSuccess) e = up(&v->trow, trow);
+    if (e == cudaSuccess) e = up(&v->tnz, tnz);
+    if (e == cudaSuccess) e = up(&v->srow, srow);
+    if (e == cudaSuccess) e = up(&v->spart, spart);
+    if (e == cudaSuccess) e = up(&v->cta_tiles, cta);
+    if (e == cudaSuccess) e = cudaMalloc(&v->part, es * (size_t) std::max(nparts, 1));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);       // the host vectors go out of scope
+    if (e != cudaSuccess){ vsplit_free(v); return hb_cuda_fail(e, "virtual-row tables"); }
+    A->vs = v;
+    return HB_OK;
+}
+
 // resident CTAs per SM of the instantiation that will run (asked of the driver, not guessed): the persistent grid and its
 // partition table are sized from it at hb_csr_create time
 template<typename T, int CFG, int TPR, bool DOT>
@@ -474,6 +608,7 @@ int hb_spmv_n_typed(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T
     const int variant = hb_spmv_variant(A);
     const double mean = A->mean_row_nnz;
     if (variant == 3){
+        if (A->vs && !(DOT && ctx->peer_hook)) return launch_pipe_vs<T, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         if (A->pipe_cfg == 0) return launch_pipe<T, 0, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         return launch_pipe<T, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
     }
@@ -612,6 +747,15 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     // heavy-tailed row lengths: equal-nnz contiguous pieces balance better than the sweep (power-law matrix: 623 vs 674 us);
     // regular matrices: the sweep keeps the gather window of x in L2/L1 (27-point: 117 vs 151 us, 512^3 7-point: -13 % DRAM traffic)
     if (A->pipe_contiguous < 0) A->pipe_contiguous = heavy_tail ? 1 : 0;
+    // heavy-tailed row lengths: long rows are cut into segments and the tiles come from a table, so that every tile is staged
+    // (HB_VSPLIT=0 keeps the general kernel with its global-memory paths: A/B probe)
+    {
+        const char *vse = getenv("HB_VSPLIT");
+        if (heavy_tail && hb_spmv_variant(A) == 3 && !(vse && vse[0] == '0')){
+            int rc = vsplit_build(ctx, A);
+            if (rc != HB_OK){ hb_csr_destroy(A); return rc; }
+        }
+    }
     *out = A;
     return HB_OK;
 }
@@ -620,6 +764,7 @@ int hb_csr_destroy(hb_csr *csr){
     if (!csr) return HB_OK;
     for (int c = 0; c < 2; c++) if (csr->cta_rows[c]) cudaFree(csr->cta_rows[c]);
     hb_tcache_delete(csr->tc);
+    vsplit_free(csr->vs);
     delete csr;
     return HB_OK;
 }

@@ -52,13 +52,23 @@ __global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int til
 // L1TEX tag stage: ncu 88 % l1tex, 44 % DRAM on the 27-point matrix), no shuffle reduction, and every row is summed left to right
 // exactly as the reference does.  A tile of ROWS = THREADS / TPR rows is walked by THREADS / NBP groups, NBP / TPR rows each; `xpf`
 // carries the number of live right-hand sides of this block (lanes beyond it compute on column 0 and store nothing).
-template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0, bool LPC = false>
+// VS ("virtual split", heavy-tailed row lengths: hb_csr_create builds the tables once): `pntr` is then the row-pointer array of a VIRTUAL
+// row set — rows longer than a segment length are cut into consecutive segments, indx / vals are the caller's arrays as they lie — and
+// tiles come from a table: tile t = virtual rows [vs.trow[t], vs.trow[t+1]) (at most ROWS of them, starts are multiples of 4) whose
+// non-zeros [vs.tnz[t], vs.tnz[t+1]) always fit one ring stage, so the global-memory paths for oversized tiles and the CTA-wide
+// reduction of very long rows never run and no CTA is left alone with a 65 536-entry row.  A virtual row that is a whole row stores
+// to y[vs.vmap[v]]; a segment stores its raw partial sum to vs.part[~vs.vmap[v]], and vsplit_combine_kernel adds the segments of each
+// split row in order afterwards (deterministic; no atomics).
+struct vsplit_view { const int *trow, *tnz, *vmap; void *part; int ntiles; };
+
+template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0, bool LPC = false, bool VS = false>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
                                                             void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
                                                             const peer_view *pv, unsigned long long epoch, size_t ldx, size_t ldy, size_t sxc,
-                                                            int trot, int twait){
+                                                            int trot, int twait, vsplit_view vs){
+    static_assert(!VS || (NBP == 0 && !LPC), "the virtual-row form is the plain product");
     constexpr int ROWS = THREADS / TPR;
     constexpr int CAP  = THREADS * pipe_slots<T>();
     constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
@@ -69,6 +79,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     __shared__ uint64_t full[STAGES];
     constexpr int BND = 64;
     __shared__ int      bnd[BND], bnd1[BND];
+    __shared__ int      brw[VS ? BND : 1], brw1[VS ? BND : 1];  // VS: first virtual row of the tile / of the next tile
     __shared__ int      stage_a0[STAGES];                   // first staged non-zero index of the tile, or -1: not staged (slow path)
     __shared__ T        red[32];
 
@@ -78,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     // behind the leading block of such rows and each CTA waits for the neighbours' flags right before its first tile at or beyond
     // virtual position `twait` (the first tile of the rotated order that touches a ghost): interior rows run while the halo is
     // still in flight, CTAs that own no boundary tile never wait.  trot = twait = 0 is a wait before the first gather.
-    bool halo_pending = (pv != nullptr);
+    bool halo_pending = DOT && (pv != nullptr);
 
     const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
     const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     // Round-robin (cta_tiles == null): CTA g takes tiles g, g+G, g+2G, ... so all CTAs sweep the matrix together and the window
     // of x they gather from stays small enough for L2 — on the 512^3 7-point problem the contiguous map re-reads x from DRAM
     // three times (ncu: 16.3 GB of traffic for 13.9 GB algorithmic), the sweep reads it once.
-    const int ntiles_all = (rows + ROWS - 1) / ROWS;
+    const int ntiles_all = VS ? vs.ntiles : (rows + ROWS - 1) / ROWS;
     const int tstride = cta_tiles ? 1 : (int) gridDim.x;
     const int tile_begin = cta_tiles ? cta_tiles[blockIdx.x] : (int) blockIdx.x;
     const int ntile = cta_tiles ? (cta_tiles[blockIdx.x + 1] - tile_begin)
@@ -110,14 +121,24 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
         // two of them per issue; a dependent global load there would put a DRAM round trip on every step's critical path
         // (all warps meet at the per-step barrier), so the ring is refilled 32 entries at a time with cp.async by the last
         // warp, a whole 16 steps before the data is waited for and 30 before it is used.
-        auto phys = [&](int j){ int t = tile_begin + j * tstride + trot; return t >= ntiles_all ? t - ntiles_all : t; };   // tile of step j
-        auto bound_src  = [&](int j){ return pntr + min((long long) phys(j) * ROWS, (long long) rows); };
-        auto bound_src1 = [&](int j){ return pntr + min(((long long) phys(j) + 1) * ROWS, (long long) rows); };
-        for (int j = tid; j < BND && j < ntile; j += THREADS){ bnd[j] = __ldg(bound_src(j)); bnd1[j] = __ldg(bound_src1(j)); }
+        // tile of step j; only the DOT form is ever rotated (the peer hooks ride on the fused SpMV + dot), the plain product keeps the
+        // index arithmetic it had
+        auto phys = [&](int j){
+            int t = tile_begin + j * tstride;
+            if constexpr (DOT && !VS){ t += trot; if (t >= ntiles_all) t -= ntiles_all; }
+            return t;
+        };
+        auto bound_src  = [&](int j){ return VS ? vs.tnz + phys(j) : pntr + min((long long) phys(j) * ROWS, (long long) rows); };
+        auto bound_src1 = [&](int j){ return VS ? vs.tnz + phys(j) + 1 : pntr + min(((long long) phys(j) + 1) * ROWS, (long long) rows); };
+        for (int j = tid; j < BND && j < ntile; j += THREADS){
+            bnd[j] = __ldg(bound_src(j)); bnd1[j] = __ldg(bound_src1(j));
+            if constexpr (VS){ brw[j] = __ldg(vs.trow + phys(j)); brw1[j] = __ldg(vs.trow + phys(j) + 1); }
+        }
         __syncthreads();
+        auto tile_r0 = [&](int k){ if constexpr (VS) return brw[k % BND]; else return phys(k) * ROWS; };
         auto issue = [&](int k, int b0, int b1){             // thread 0 only; b0,b1 = non-zero bounds of tile k
             const int s = k % STAGES;
-            const int r0 = phys(k) * ROWS;
+            const int r0 = tile_r0(k);
             T *sv = stage_vals(s); int *sc = stage_cols(s); int *sp = stage_ptr(s);
             // pntr slice [r0, r0 + PSL) clipped to the array; ragged end by hand
             const int pend = min(r0 + PSL, rows + 1);
@@ -152,24 +173,31 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             if (tid >= THREADS - 32){                           // ring refill by the last warp (see above)
                 if ((k & 31) == 0 && k > 0){
                     const int j = k + 32 + (tid & 31);
-                    if (j < ntile){ cp_async4(&bnd[j % BND], bound_src(j)); cp_async4(&bnd1[j % BND], bound_src1(j)); }
+                    if (j < ntile){
+                        cp_async4(&bnd[j % BND], bound_src(j)); cp_async4(&bnd1[j % BND], bound_src1(j));
+                        if constexpr (VS){ cp_async4(&brw[j % BND], vs.trow + phys(j)); cp_async4(&brw1[j % BND], vs.trow + phys(j) + 1); }
+                    }
                     cp_async_commit();
                 }else if ((k & 31) == 16){
                     cp_async_wait_all();                        // published to thread 0 by this step's closing barrier
                 }
             }
-            if (halo_pending && tile_begin + k * tstride >= twait){        // block-uniform
+            if (DOT && halo_pending && tile_begin + k * tstride >= twait){ // block-uniform
                 if (tid < 32) peer_halo_wait(pv, epoch);
                 __syncthreads();
                 halo_pending = false;
             }
             mbar_wait(full + s, (uint32_t) ((k / STAGES) & 1));
-            const int r0 = phys(k) * ROWS;
+            const int r0 = tile_r0(k);
             const int myrow = r0 + grp;
             const int *sp = stage_ptr(s);
             const int a0 = stage_a0[s];
             int rs = 0, re = 0;
-            if (myrow < rows){ rs = sp[grp]; re = sp[grp + 1]; }
+            bool live_row = myrow < rows;
+            if constexpr (VS) live_row = grp < brw1[k % BND] - r0;
+            int vdst = 0;                                       // VS: where this virtual row's sum goes (loaded early, used after the sweep)
+            if constexpr (VS){ if (live_row && sub == 0) vdst = __ldg(vs.vmap + myrow); }
+            if (live_row){ rs = sp[grp]; re = sp[grp + 1]; }
             T sum = zero_of<T>();
             if constexpr (NBP > 0 && LPC){
                 constexpr int GROUPS = THREADS / NBP, RPG = ROWS / GROUPS, MU = (sizeof(T) == 16 ? 4 : 8);
@@ -326,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                     part = shfl_from(warp_sum(hadd(part, part2)), 0);      // warp_sum leaves the total in lane 0
                     if ((tid & 31) == src) sum = part;
                 }
-                const int rlast = min(r0 + ROWS, rows);
+                const int rlast = min(r0 + ROWS, rows);         // (VS never gets here: every tile of the table fits its stage)
                 for (int r = r0; r < rlast; r++){
                     const int ls = sp[r - r0], le = sp[r - r0 + 1];
                     if (le - ls < PIPE_LONGROW) continue;       // block-uniform: sp is shared
@@ -341,7 +369,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             }
             #pragma unroll
             for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
-            if (sub == 0 && myrow < rows){
+            if constexpr (VS){
+                if (sub == 0 && live_row){
+                    if (vdst < 0){
+                        reinterpret_cast<T*>(vs.part)[~vdst] = sum;    // a segment: raw partial sum, combined afterwards
+                    }else if (DOT){
+                        y[vdst] = sum;
+                        dot_acc = hfma(hconj(ld_ro(x + vdst)), sum, dot_acc);
+                    }else{
+                        T out = hmul(alpha, sum);
+                        if (use_beta) out = hfma(beta, y[vdst], out);
+                        y[vdst] = out;
+                    }
+                }
+            }else if (sub == 0 && myrow < rows){
                 if (DOT){
                     y[myrow] = sum;
                     dot_acc = hfma(hconj(ld_ro(x + myrow)), sum, dot_acc);
@@ -370,6 +411,46 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                 if (poisoned) out = from_real<T>((real_t<T>) __longlong_as_double(0x7ff8000000000000LL));
                 if (tid < 32) peer_publish<T>(pv, HB_PEER_CH_PAP, epoch, out);
             }
+        }
+    }
+}
+
+// VS tail: y[row] = alpha * (sum of the row's segment partials, in order) + beta * y[row] for the split rows; with DOT, y[row] = sum and
+// *dot_out += sum over split rows of conj(x[row]) y[row] (added by the last block, after the streaming kernel wrote its own total).
+// One warp per split row: lanes stride over the row's parts, shuffle reduction — the same order every time.
+template<typename T, bool DOT>
+__global__ void __launch_bounds__(256) vsplit_combine_kernel(int nsplit, const int * __restrict__ srow, const int * __restrict__ spart, const T * __restrict__ part,
+                                                            scalar_arg<T> alpha_s, scalar_arg<T> beta_s, T *y, const T * __restrict__ x,
+                                                            void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag){
+    __shared__ T red[32];
+    if (skip_flag && *skip_flag) return;
+    const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
+    const bool use_beta = !hiszero(beta);
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    T dot_acc = zero_of<T>();
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nsplit; i += gridDim.x * wpb){
+        const int p0 = spart[i], p1 = spart[i + 1], row = srow[i];
+        T acc = zero_of<T>();
+        for (int j = p0 + lane; j < p1; j += 32) acc = hadd(acc, part[j]);
+        acc = warp_sum(acc);
+        if (lane == 0){
+            if (DOT){
+                y[row] = acc;
+                dot_acc = hfma(hconj(ld_ro(x + row)), acc, dot_acc);
+            }else{
+                T out = hmul(alpha, acc);
+                if (use_beta) out = hfma(beta, y[row], out);
+                y[row] = out;
+            }
+        }
+    }
+    if (DOT){
+        T *partials = reinterpret_cast<T*>(partials_v);
+        T b = block_sum(dot_acc, red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = b;
+        if (last_block_arrives(ticket)){
+            T total = sum_partials<T>(partials, gridDim.x, 1, red);
+            if (threadIdx.x == 0) *dot_out = hadd(*dot_out, total);
         }
     }
 }
