@@ -59,10 +59,10 @@ static constexpr int    HB_MAX_GRID      = 148 * 16;   // persistent-style grids
 struct hb_tcache;                       // cached transposed copy behind op 'T' / 'C' (hb_transpose.cu)
 // heavy-tailed row lengths: virtual-row view + tile table of the streaming kernel (hb_spmv_pipe.cuh, VS form); all arrays on the device
 struct hb_vsplit {
-    int nvrows = 0, ntiles = 0, nsplit = 0, nparts = 0, seg = 0, tpr = 2, grid = 0;
+    int nvrows = 0, ntiles = 0, nsplit = 0, nparts = 0, seg = 0, tpr = 2, grid = 0, contiguous = 0;
     int *vpntr = nullptr;               // nvrows + 1: row pointers of the virtual rows (into the caller's indx / vals)
     int *vmap = nullptr;                // nvrows: >= 0 the real row this virtual row IS; < 0: ~index of its slot in `part`
-    int *trow = nullptr, *tnz = nullptr;// ntiles + 1: first virtual row / first non-zero of tile t
+    int *trow = nullptr, *tnz = nullptr;// ntiles + 1: first virtual row (a multiple of 4; bit 0 set: the tile holds long rows) / first non-zero of tile t
     int *srow = nullptr, *spart = nullptr;  // nsplit: the split rows; nsplit + 1: first slot of each in `part`
     void *part = nullptr;               // nparts partial sums (scalars of the matrix type)
     int *cta_tiles = nullptr;           // grid + 1: contiguous equal-nnz pieces of the tile list

@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(DK_THREADS) dcg_direction_kernel(int n, cg_dst
 //              their ghost slots of buffer (g+1)&1 (recomputed from r and the old p, so no grid-wide dependency) and releases
 //              the flags of g+1, THEN sweeps x += a p_old, p_new = r + b p_old.  p ping-pongs between two buffers, which is
 //              what makes the early push legal and double-buffers the ghost slots for free.
-static constexpr int PK_MIN_GRID = HB_HALO_BLOCKS;
 
 __global__ void peer_halo_wait_kernel(const peer_view *pv, unsigned long long g, const int *skip){
     if (skip && *skip) return;
@@ -198,9 +197,9 @@ template<typename T> __global__ void peer_publish_kernel(const peer_view *pv, in
 // after the NCCL all-reduce of the setup's <r,r>: zr[0], ||r||, and the halo of the first direction p = r
 template<typename T>
 __global__ void __launch_bounds__(DK_THREADS) pcg_begin_kernel(cg_dstate<T> *st, const peer_view *pv, unsigned long long g,
-                                                               const int * __restrict__ send_idx, const T * __restrict__ p){
+                                                               const int * __restrict__ send_idx, const T * __restrict__ p, unsigned int *ticket){
     if (blockIdx.x == 0 && threadIdx.x == 0){ st->zr[0] = st->rr; st->rnorm = sqrt((double) hreal(st->rr)); }
-    peer_halo_push<T>(pv, g, [&](int j){ return p[send_idx[j]]; });
+    peer_halo_push<T>(pv, g, ticket, [&](int j){ return p[send_idx[j]]; });
 }
 template<typename T, bool VEC>
 __global__ void __launch_bounds__(DK_THREADS, 4) pcg_update_kernel(int n, cg_dstate<T> *st, int parity, unsigned long long g, const T * __restrict__ q,
@@ -242,7 +241,8 @@ __global__ void __launch_bounds__(DK_THREADS, 4) pcg_update_kernel(int n, cg_dst
 template<typename T, bool VEC>
 __global__ void __launch_bounds__(DK_THREADS, 4) pcg_direction_kernel(int n, cg_dstate<T> *st, int parity, unsigned long long g, int it_now,
                                                                       const T * __restrict__ r, const T * __restrict__ p_old, T *p_new, T *x,
-                                                                      const peer_view *pv, const int * __restrict__ send_idx, cg_dhost *host){
+                                                                      const peer_view *pv, const int * __restrict__ send_idx, cg_dhost *host,
+                                                                      unsigned int *ticket){
     __shared__ double s_rr;
     if (st->done[parity]){
         if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(DK_THREADS, 4) pcg_direction_kernel(int n, cg_
     const vec16<T> *r4 = reinterpret_cast<const vec16<T>*>(r), *po4 = reinterpret_cast<const vec16<T>*>(p_old);
     if (!stop){
         const T beta = hdiv(rr, zr);
-        peer_halo_push<T>(pv, g + 1, [&](int j){ const int i = send_idx[j]; return hfma(beta, p_old[i], r[i]); });
+        peer_halo_push<T>(pv, g + 1, ticket, [&](int j){ const int i = send_idx[j]; return hfma(beta, p_old[i], r[i]); });
         stream_sweep<T, VEC, U>((size_t) n,
             [&](int u, size_t i){ vx[u] = x4[i]; vp[u] = po4[i]; vr[u] = r4[i]; },
             [&](int u, size_t i){
@@ -295,6 +295,12 @@ __global__ void __launch_bounds__(DK_THREADS, 4) pcg_direction_kernel(int n, cg_
 // ------------------------------------------------------------------------------------------------ helpers
 static ncclDataType_t real_dtype(int dtype){ return (dtype == HB_F32 || dtype == HB_C32) ? ncclFloat32 : ncclFloat64; }
 static int reals_per_scalar(int dtype){ return (dtype == HB_C32 || dtype == HB_C64) ? 2 : 1; }
+// blocks of a stand-alone halo push: two entries per thread, at most two blocks per SM
+static int halo_grid(const hb_ctx *ctx, long long send_total){
+    long long need = (send_total + 511) / 512, cap = (long long) ctx->num_sms * 2;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
 static int dgrid(const hb_ctx *ctx, long long n, int per_block){
     long long need = (n + per_block - 1) / per_block, cap = (long long) ctx->num_sms * 4;
     if (need < 1) need = 1;
@@ -491,8 +497,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
     cg_dhost *hstat = reinterpret_cast<cg_dhost*>(reinterpret_cast<char*>(ctx->hscalars) + 512);
     void *hstat_dev = reinterpret_cast<char*>(ctx->hscalars_dev) + 512;
     hstat->done = 0; hstat->iterations = 0; hstat->rnorm = 0;
-    int grid = dgrid(ctx, n, DK_THREADS * 8);
-    if (grid < PK_MIN_GRID) grid = PK_MIN_GRID;
+    const int grid = dgrid(ctx, n, DK_THREADS * 8);
     const bool fused = peer_env_fused_spmv() && hb_spmv_variant(A) == 3;
     const peer_view *pv = d->pv_dev;
     int trot = 0, twait = 0;
@@ -518,7 +523,7 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
                                                                                            ctx->partials, ctx->tickets + 6);
         HB_LAUNCH_CHECK(ctx);
         if ((rc = hb_dist_allreduce_sum_nccl(d, dtype, &st->rr, 1)) != HB_OK) return rc;
-        pcg_begin_kernel<T><<<HB_HALO_BLOCKS, DK_THREADS, 0, ctx->stream>>>(st, pv, g0, d->send_idx, (const T*) p0);
+        pcg_begin_kernel<T><<<halo_grid(ctx, d->send_total), DK_THREADS, 0, ctx->stream>>>(st, pv, g0, d->send_idx, (const T*) p0, ctx->tickets + 8);
         HB_LAUNCH_CHECK(ctx);
     });
 
@@ -560,9 +565,9 @@ int dist_cg_peer(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol
                 ctx->launches++;
                 hb_prof_mark(ctx, it, 2);
                 if (vec) pcg_direction_kernel<T, true><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
-                                                                                             pv, d->send_idx, (cg_dhost*) hstat_dev);
+                                                                                             pv, d->send_idx, (cg_dhost*) hstat_dev, ctx->tickets + 8);
                 else     pcg_direction_kernel<T, false><<<grid, DK_THREADS, 0, ctx->stream>>>(n, st, parity, g, it_now, (const T*) r, (const T*) p_old, (T*) p_new, (T*) x,
-                                                                                              pv, d->send_idx, (cg_dhost*) hstat_dev);
+                                                                                              pv, d->send_idx, (cg_dhost*) hstat_dev, ctx->tickets + 8);
                 ctx->launches++;
                 hb_prof_mark(ctx, it, 3);
             });
@@ -738,7 +743,7 @@ int hb_dist_halo_exchange(hb_dist *d, int dtype, void *x_ext){
     const unsigned long long g = d->epoch++;
     char *pb = (char*) d->pbuf + HB_MAILBOX_BYTES + (size_t) (g & 1) * d->pbuf_ext_bytes;
     HB_DISPATCH(dtype, {
-        peer_vec_push_kernel<T><<<HB_HALO_BLOCKS, 256, 0, ctx->stream>>>(d->pv_dev, g, d->send_idx, (const T*) x_ext);
+        peer_vec_push_kernel<T><<<halo_grid(ctx, d->send_total), 256, 0, ctx->stream>>>(d->pv_dev, g, d->send_idx, (const T*) x_ext, ctx->tickets + 8);
         ctx->launches++;
         const int grid = dgrid(ctx, d->n_ghost, 256 * 4);
         peer_vec_pull_kernel<T><<<grid, 256, 0, ctx->stream>>>(d->pv_dev, g, (const T*) pb + d->n_owned, (T*) x_ext + d->n_owned, d->n_ghost);

@@ -16,7 +16,7 @@
 
 static constexpr int HB_MAX_PEERS   = 16;      // ranks of one NVLink domain (8 on an HGX B200 board)
 static constexpr int HB_MAX_NEIGH   = 8;       // halo neighbours per rank on this path (1-D row blocks of a stencil: 2)
-static constexpr int HB_HALO_BLOCKS = 32;      // blocks that push the halo, each signalling its own flag
+static constexpr int HB_HALO_BLOCKS = 32;      // flag slots per source rank in the mailbox (slot 0 is the one in use)
 static constexpr int HB_PEER_CH_PAP = 0, HB_PEER_CH_RR = 1;
 
 struct peer_slot { double v[2]; unsigned long long seq; unsigned long long pad; };              // 32 B
@@ -118,32 +118,29 @@ template<typename T> __device__ __forceinline__ T peer_wait_sum(const peer_view 
     }
     return slot_unpack<T>(sa, sb);
 }
-// Called by the first warp of a block (converged): waits until every neighbour that sends us ghosts has released all of its
-// HB_HALO_BLOCKS flags for epoch g.  Returns false on time-out (mailbox marked).
+// Called by the first warp of a block (converged): waits until every neighbour that sends us ghosts has released its flag for
+// epoch g (one flag per neighbour: the LAST of the neighbour's pushing blocks releases it).  Returns false on time-out (mailbox marked).
 __device__ __forceinline__ bool peer_halo_wait(const peer_view *pv, unsigned long long g){
     const int lane = threadIdx.x & 31;
     peer_mailbox *mine = pv->mail[pv->rank];
     bool ok = true;
-    for (int k = 0; k < pv->nneigh; k++){
-        if (!pv->recv_from[k]) continue;
-        for (int b = lane; b < HB_HALO_BLOCKS; b += 32)
-            ok = peer_spin(&mine->halo_seq[pv->neigh[k]][b], g + 1, pv->timeout_clocks) && ok;
-    }
+    for (int k = lane; k < pv->nneigh; k += 32)
+        if (pv->recv_from[k]) ok = peer_spin(&mine->halo_seq[pv->neigh[k]][0], g + 1, pv->timeout_clocks);
     ok = __all_sync(0xffffffffu, ok);
     if (!ok && lane == 0) mine->error = 1;
     return ok;
 }
-// Halo push by blocks 0 .. HB_HALO_BLOCKS-1 of a grid (every thread of those blocks calls it, converged per block).
-// value(j) = the new p entry at local index send_idx[j]; entry j of the concatenated send list goes to neighbour k with
-// send_off[k] <= j < send_off[k+1], into its ghost slot of buffer parity (g & 1).  Each block then releases its flag g + 1 in
-// every neighbour's mailbox (blocks with an empty chunk as well: the receiver counts flags, not data).
+// Halo push by ALL blocks of a grid (every thread of every block calls it, converged per block).  value(j) = the new entry at local
+// index send_idx[j]; entry j of the concatenated send list goes to neighbour k with send_off[k] <= j < send_off[k+1], into its ghost
+// slot of buffer parity (g & 1).  The list is dealt over the whole grid (a few entries per thread: the push is a chain of dependent
+// loads and a remote store, so 32 blocks walking 16 K entries each took ~50 us of the direction kernel at 8 GPUs; the whole grid takes
+// a few).  Every block fences its stores at system scope and takes a ticket; the block that takes the last one releases ONE flag
+// g + 1 per neighbour.  `ticket` is a device counter that is zero between kernels (re-armed by the last block).
 template<typename T, typename F>
-__device__ __forceinline__ void peer_halo_push(const peer_view *pv, unsigned long long g, F value){
-    if (blockIdx.x >= HB_HALO_BLOCKS) return;
+__device__ __forceinline__ void peer_halo_push(const peer_view *pv, unsigned long long g, unsigned int *ticket, F value){
     const int total = pv->send_off[pv->nneigh];
-    const int chunk = (total + HB_HALO_BLOCKS - 1) / HB_HALO_BLOCKS;
-    const int j0 = blockIdx.x * chunk, j1 = min(j0 + chunk, total);
-    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x){
+    if (total == 0) return;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x){
         int k = 0;
         while (j >= pv->send_off[k + 1]) k++;
         T *dst = reinterpret_cast<T*>(pv->ghost_dst[k][g & 1]) + (j - pv->send_off[k]);
@@ -151,8 +148,15 @@ __device__ __forceinline__ void peer_halo_push(const peer_view *pv, unsigned lon
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x < pv->nneigh && pv->send_off[threadIdx.x + 1] > pv->send_off[threadIdx.x])
-        st_release_sys(&pv->mail[pv->neigh[threadIdx.x]]->halo_seq[pv->rank][blockIdx.x], g + 1);
+    if (threadIdx.x == 0){
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1){
+            *ticket = 0;
+            __threadfence_system();
+            for (int k = 0; k < pv->nneigh; k++)
+                if (pv->send_off[k + 1] > pv->send_off[k]) st_release_sys(&pv->mail[pv->neigh[k]]->halo_seq[pv->rank][0], g + 1);
+        }
+    }
 }
 
 // In-place sum over ranks of `count` (<= HB_PEER_VMAX) scalars that live on the device: ONE block.  Every rank stores its values
@@ -193,8 +197,9 @@ __global__ void __launch_bounds__(128) peer_allsum_kernel(const peer_view *pv, u
 // Halo of an arbitrary vector v_ext = [owned | ghosts] (GMRES basis vectors): push = our boundary entries into the neighbours' ghost
 // slots of exchange buffer (g & 1) + flags; pull = wait for the neighbours' flags, then copy our ghost slots behind the owned part.
 template<typename T>
-__global__ void __launch_bounds__(256) peer_vec_push_kernel(const peer_view *pv, unsigned long long g, const int * __restrict__ send_idx, const T * __restrict__ v){
-    peer_halo_push<T>(pv, g, [&](int j){ return v[send_idx[j]]; });
+__global__ void __launch_bounds__(256) peer_vec_push_kernel(const peer_view *pv, unsigned long long g, const int * __restrict__ send_idx, const T * __restrict__ v,
+                                                            unsigned int *ticket){
+    peer_halo_push<T>(pv, g, ticket, [&](int j){ return v[send_idx[j]]; });
 }
 template<typename T>
 __global__ void __launch_bounds__(256) peer_vec_pull_kernel(const peer_view *pv, unsigned long long g, const T *ghost_src, T *ghost_dst, int n_ghost){

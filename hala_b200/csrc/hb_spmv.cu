@@ -469,7 +469,7 @@ static int launch_pipe_vs_tpr(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, sc
     vsplit_view view;
     view.trow = v->trow; view.tnz = v->tnz; view.vmap = v->vmap; view.part = v->part; view.ntiles = v->ntiles;
     k<<<v->grid, VS_THREADS, smem, ctx->stream>>>(v->nvrows, A->nnz, v->vpntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
-                                                  A->pipe_contiguous ? v->cta_tiles : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip, 0, A->cols,
+                                                  v->contiguous ? v->cta_tiles : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip, 0, A->cols,
                                                   nullptr, 0ull, (size_t) 0, (size_t) 0, (size_t) 0, 0, 0, view);
     HB_LAUNCH_CHECK(ctx);
     if (v->nsplit > 0){
@@ -530,13 +530,15 @@ static int vsplit_build(hb_ctx *ctx, hb_csr *A){
             r = r4;
         }
         if (r == t0){ hb_set_error("internal: a group of four virtual rows exceeds a ring stage"); return HB_ERR_ARG; }
-        trow.push_back(t0);
+        int has_long = 0;                                       // bit 0 of the table entry: the tile holds a row the warp path takes
+        for (int q = t0; q < r && !has_long; q++) has_long = (vpntr[(size_t) q + 1] - vpntr[(size_t) q]) >= PIPE_WARPROW;
+        trow.push_back(t0 | has_long);
         t0 = r;
     }
-    trow.push_back(nv);
+    trow.push_back(nv % 4 == 0 ? nv : ((nv + 3) & ~3));         // end marker, rounded up so that masking the flag bits keeps it >= nv
     const int nt = (int) trow.size() - 1;
     tnz.resize(trow.size());
-    for (size_t t = 0; t < trow.size(); t++) tnz[t] = vpntr[(size_t) trow[t]];
+    for (size_t t = 0; t < trow.size(); t++) tnz[t] = vpntr[(size_t) std::min(trow[t] & ~3, nv)];
     int G = ctx->num_sms * occ;
     if (G > nt) G = nt;
     std::vector<int> cta((size_t) G + 1);
@@ -545,6 +547,10 @@ static int vsplit_build(hb_ctx *ctx, hb_csr *A){
         cta[(size_t) g] = g == G ? nt : (int) (std::lower_bound(tnz.begin(), tnz.begin() + nt, (int) target) - tnz.begin());
     }
     hb_vsplit *v = new hb_vsplit();
+    {   // tiles hold about the same number of non-zeros: dealt round-robin (HB_PIPE_MAP=c: contiguous equal-nnz pieces)
+        const char *m = getenv("HB_PIPE_MAP");
+        v->contiguous = (m && m[0] == 'c') ? 1 : 0;
+    }
     v->nvrows = nv; v->ntiles = nt; v->nsplit = (int) srow.size(); v->nparts = nparts; v->seg = seg; v->tpr = tpr; v->grid = G;
     auto up = [&](int **dst, const std::vector<int> &src)->cudaError_t{
         cudaError_t e = cudaMalloc((void**) dst, sizeof(int) * std::max<size_t>(src.size(), 4));

@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     __shared__ uint64_t full[STAGES];
     constexpr int BND = 64;
     __shared__ int      bnd[BND], bnd1[BND];
-    __shared__ int      brw[VS ? BND : 1], brw1[VS ? BND : 1];  // VS: first virtual row of the tile / of the next tile
+    __shared__ int      brw[VS ? BND : 1], brw1[VS ? BND : 1];  // VS: first virtual row of the tile (bit 0: the tile holds long rows) / of the next tile
+    __shared__ int      vl_count, vl_row[VS ? ROWS : 1];        // VS: long rows of the current tile, dealt over ALL warps of the CTA
+    __shared__ T        vl_sum[VS ? ROWS : 1];
     __shared__ int      stage_a0[STAGES];                   // first staged non-zero index of the tile, or -1: not staged (slow path)
     __shared__ T        red[32];
 
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             if constexpr (VS){ brw[j] = __ldg(vs.trow + phys(j)); brw1[j] = __ldg(vs.trow + phys(j) + 1); }
         }
         __syncthreads();
-        auto tile_r0 = [&](int k){ if constexpr (VS) return brw[k % BND]; else return phys(k) * ROWS; };
+        auto tile_r0 = [&](int k){ if constexpr (VS) return brw[k % BND] & ~3; else return phys(k) * ROWS; };
         auto issue = [&](int k, int b0, int b1){             // thread 0 only; b0,b1 = non-zero bounds of tile k
             const int s = k % STAGES;
             const int r0 = tile_r0(k);
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             const int a0 = stage_a0[s];
             int rs = 0, re = 0;
             bool live_row = myrow < rows;
-            if constexpr (VS) live_row = grp < brw1[k % BND] - r0;
+            if constexpr (VS) live_row = grp < (brw1[k % BND] & ~3) - r0 && myrow < rows;
+            const bool tile_has_long = VS && (brw[k % BND] & 1);  // block-uniform, from the tile table
             int vdst = 0;                                       // VS: where this virtual row's sum goes (loaded early, used after the sweep)
             if constexpr (VS){ if (live_row && sub == 0) vdst = __ldg(vs.vmap + myrow); }
             if (live_row){ rs = sp[grp]; re = sp[grp + 1]; }
@@ -312,9 +315,34 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                     }
                 }
                 sum = hadd(sum, sum2);
+                // VS: a tile made of long segments has only a handful of rows, all owned by the first lanes of warp 0 — deal the long
+                // rows of the tile over all warps of the CTA instead (the tile table says which tiles have any: no barrier elsewhere)
+                if (tile_has_long){
+                    if (tid == 0) vl_count = 0;
+                    __syncthreads();
+                    if (wlong && sub == 0) vl_row[atomicAdd(&vl_count, 1)] = grp;
+                    __syncthreads();
+                    const int nl = vl_count;
+                    for (int q = tid >> 5; q < nl; q += THREADS / 32){
+                        const int lr = vl_row[q], ls = sp[lr] - a0, le = sp[lr + 1] - a0;
+                        T part = zero_of<T>(), part2 = zero_of<T>();
+                        int j = ls + (tid & 31);
+                        for (; j + 96 < le; j += 128){
+                            const int c0 = sc[j], c1 = sc[j + 32], c2 = sc[j + 64], c3 = sc[j + 96];
+                            const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
+                            part = hfma(sv[j], x0, part); part2 = hfma(sv[j + 32], x1, part2);
+                            part = hfma(sv[j + 64], x2, part); part2 = hfma(sv[j + 96], x3, part2);
+                        }
+                        for (; j < le; j += 32) part = hfma(sv[j], ld_ro(x + sc[j]), part);
+                        part = warp_sum(hadd(part, part2));
+                        if ((tid & 31) == 0) vl_sum[lr] = part;
+                    }
+                    __syncthreads();
+                    if (wlong && sub == 0) sum = vl_sum[grp];
+                }
                 // warp-cooperative pass over this warp's long rows (heavy-tailed row lengths): 32 lanes stride over the row in
                 // shared memory, four entries per lane in flight, shuffle reduction; the owner lane (sub == 0) keeps the sum
-                unsigned todo = __ballot_sync(0xffffffffu, wlong && sub == 0);
+                unsigned todo = __ballot_sync(0xffffffffu, !tile_has_long && wlong && sub == 0);
                 while (todo){
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
