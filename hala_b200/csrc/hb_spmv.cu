@@ -294,8 +294,8 @@ static int launch_rowvec(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_
 template<int CFG> struct pipe_cfg;
 template<> struct pipe_cfg<0> { static constexpr int THREADS = 128, STAGES = 3; };
 template<> struct pipe_cfg<1> { static constexpr int THREADS = 256, STAGES = 3; };
-static size_t pipe_smem_bytes(int threads, int tpr, int stages, size_t es){
-    const size_t cap = (size_t) threads * (es == 16 ? 4 : 8), rows = threads / tpr;
+static size_t pipe_smem_bytes(int threads, int tpr, int stages, size_t es, int slot_div = 1){
+    const size_t cap = (size_t) threads * (es == 16 ? 4 : 8) / slot_div, rows = threads / tpr;
     return stages * ((cap + 4) * (es + sizeof(int)) + (rows + 4) * sizeof(int));
 }
 // lanes per row: the smallest power of two that keeps a typical row within ~7 entries per lane (<= two batches of four)
@@ -431,8 +431,29 @@ int hb_spmm_interleaved(hb_ctx *ctx, const hb_csr *A, int nbp, const void *Bt, s
     return HB_OK;
 }
 
+// Shared memory and L1 share one 256 KB array per SM, and every gather of x that misses L1 needs an L1 line to land in: a kernel that
+// takes all the shared memory it can leaves ~30 KB of L1, i.e. a couple of hundred misses in flight per SM, and the x gather then runs
+// at a fraction of what the L1TEX pipe can do (power-law matrix: 548 us with the largest carve-out, of which 383 us are the gathers).
+// So the carve-out is set to what `want` resident CTAs need and no more; want <= 0: as many CTAs as fit (largest carve-out).
+// Returns the number of CTAs per SM to size the grid with.
+template<typename K>
+static int pipe_configure(K kernel, int threads, size_t smem, int want){
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    int carve = cudaSharedmemCarveoutMaxShared;
+    if (want > 0){
+        const double need = (double) want * (double) (smem + 4096) / (228.0 * 1024.0) * 100.0;     // + static shared memory and the per-CTA reserve
+        carve = need >= 100.0 ? 100 : (int) (need + 0.999);
+    }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess){ cudaGetLastError(); return 0; }
+    return (want > 0 && n > want) ? want : n;
+}
+static int env_int(const char *name, int dflt){ const char *e = getenv(name); return e ? atoi(e) : dflt; }
+
 // ---- heavy-tailed row lengths: virtual-row / tile-table form of the streaming kernel (spmv_pipe_kernel<..., VS = true>)
-static constexpr int VS_THREADS = pipe_cfg<0>::THREADS, VS_STAGES = pipe_cfg<0>::STAGES;
+static constexpr int VS_THREADS = pipe_cfg<0>::THREADS, VS_STAGES = 2;
+static constexpr int VS_CTAS = 5;          // resident CTAs per SM the carve-out is sized for (HB_VS_CTAS overrides): the rest of the array is L1 for the gathers
 static void vsplit_free(hb_vsplit *v){
     if (!v) return;
     for (void *p : {(void*) v->vpntr, (void*) v->vmap, (void*) v->trow, (void*) v->tnz, (void*) v->srow, (void*) v->spart, v->part, (void*) v->cta_tiles})
@@ -441,35 +462,33 @@ static void vsplit_free(hb_vsplit *v){
 }
 template<typename T, int TPR, bool DOT>
 static int vsplit_occupancy(){
-    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T));
+    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T), VS_SLOT_DIV);
     auto k = spmv_pipe_kernel<T, VS_THREADS, TPR, VS_STAGES, DOT, 0, false, true>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess){ cudaGetLastError(); return 0; }
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, VS_THREADS, smem) != cudaSuccess){ cudaGetLastError(); return 0; }
-    return n;
+    return pipe_configure(k, VS_THREADS, smem, env_int("HB_VS_CTAS", VS_CTAS));
 }
 static int vsplit_occupancy_any(int dtype, int tpr){
     HB_DISPATCH(dtype, {
         int a = 0, b = 0;
         switch (tpr){
-            case 8:  a = vsplit_occupancy<T, 8, false>(); b = vsplit_occupancy<T, 8, true>(); break;
             case 4:  a = vsplit_occupancy<T, 4, false>(); b = vsplit_occupancy<T, 4, true>(); break;
-            default: a = vsplit_occupancy<T, 2, false>(); b = vsplit_occupancy<T, 2, true>(); break;
+            case 2:  a = vsplit_occupancy<T, 2, false>(); b = vsplit_occupancy<T, 2, true>(); break;
+            default: a = vsplit_occupancy<T, 1, false>(); b = vsplit_occupancy<T, 1, true>(); break;
         }
         return a < b ? a : b;
     });
     return 0;
 }
+// measurement probe (results are WRONG with it on): bit 0 skips the row sums, bit 1 replaces the gathers of x by a constant
+static int vs_probe_bits(){ const char *e = getenv("HB_VS_PROBE"); return e ? atoi(e) & 3 : 0; }
 template<typename T, int TPR, bool DOT>
 static int launch_pipe_vs_tpr(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
     const hb_vsplit *v = A->vs;
-    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T));
+    const size_t smem = pipe_smem_bytes(VS_THREADS, TPR, VS_STAGES, sizeof(T), VS_SLOT_DIV);
     auto k = spmv_pipe_kernel<T, VS_THREADS, TPR, VS_STAGES, DOT, 0, false, true>;
     vsplit_view view;
     view.trow = v->trow; view.tnz = v->tnz; view.vmap = v->vmap; view.part = v->part; view.ntiles = v->ntiles;
     k<<<v->grid, VS_THREADS, smem, ctx->stream>>>(v->nvrows, A->nnz, v->vpntr, A->indx, (const T*) A->vals, x, y, alpha, beta,
-                                                  v->contiguous ? v->cta_tiles : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip, 0, A->cols,
+                                                  v->contiguous ? v->cta_tiles : nullptr, ctx->partials, ctx->tickets + 1, dot_out, skip, vs_probe_bits(), A->cols,
                                                   nullptr, 0ull, (size_t) 0, (size_t) 0, (size_t) 0, 0, 0, view);
     HB_LAUNCH_CHECK(ctx);
     if (v->nsplit > 0){
@@ -483,9 +502,9 @@ static int launch_pipe_vs_tpr(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, sc
 template<typename T, bool DOT>
 static int launch_pipe_vs(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
     switch (A->vs->tpr){
-        case 8:  return launch_pipe_vs_tpr<T, 8, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
         case 4:  return launch_pipe_vs_tpr<T, 4, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
-        default: return launch_pipe_vs_tpr<T, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        case 2:  return launch_pipe_vs_tpr<T, 2, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
+        default: return launch_pipe_vs_tpr<T, 1, DOT>(ctx, A, x, y, alpha, beta, dot_out, skip);
     }
 }
 // One-time analysis on the host (heavy-tailed matrices only: one 4(rows+1)-byte read-back, two linear host loops, ~35 MB of tables for the
@@ -493,8 +512,11 @@ static int launch_pipe_vs(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar
 // and tiles can start at multiples of four virtual rows (16-byte aligned slices of vpntr for the bulk copies).
 static int vsplit_build(hb_ctx *ctx, hb_csr *A){
     const size_t es = hb_dtype_size(A->dtype);
-    const int cap = VS_THREADS * (es == 16 ? 4 : 8);
-    int tpr = A->tpr < 2 ? 2 : (A->tpr > 8 ? 8 : A->tpr);
+    const int cap = VS_THREADS * (es == 16 ? 4 : 8) / VS_SLOT_DIV;
+    // lanes per row of the summation phase only (the gathers are dealt by non-zero): half of what the general kernel would take, so
+    // that tiles are filled by non-zeros rather than cut short by the row limit; HB_VS_TPR overrides (probe)
+    int tpr = A->tpr / 2 < 1 ? 1 : (A->tpr / 2 > 4 ? 4 : A->tpr / 2);
+    { const char *te = getenv("HB_VS_TPR"); if (te){ const int q = atoi(te); if (q == 1 || q == 2 || q == 4) tpr = q; } }
     const int occ = vsplit_occupancy_any(A->dtype, tpr);
     if (occ < 1) return HB_OK;                                  // cannot run here: the matrix keeps the general kernel
     const int tile_rows = VS_THREADS / tpr, seg = ((cap - 8) / 4) & ~3;
@@ -578,11 +600,7 @@ static int pipe_occupancy_one(){
     using C = pipe_cfg<CFG>;
     const size_t smem = pipe_smem_bytes(C::THREADS, TPR, C::STAGES, sizeof(T));
     auto k = spmv_pipe_kernel<T, C::THREADS, TPR, C::STAGES, DOT>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess){ cudaGetLastError(); return 0; }
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, C::THREADS, smem) != cudaSuccess){ cudaGetLastError(); return 0; }
-    return n;
+    return pipe_configure(k, C::THREADS, smem, env_int("HB_PIPE_CTAS", 0));
 }
 template<typename T, int CFG>
 static int pipe_occupancy(int tpr){

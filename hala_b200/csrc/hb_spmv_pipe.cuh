@@ -23,6 +23,10 @@
 
 // ring capacity per stage = THREADS * pipe_slots<T>() non-zeros; entries per lane per batch = the same number
 template<typename T> __host__ __device__ constexpr int pipe_slots(){ return sizeof(T) == 16 ? 4 : 8; }
+// the virtual-row form (VS) keeps its stages small: its gathers are random, every miss needs an L1 line to land in, and shared memory
+// is carved out of the same array as L1 (see pipe_configure in hb_spmv.cu)
+static constexpr int VS_SLOT_DIV = 1;   // (halved stages were tried: more barriers per non-zero, 351 us against 305 us on the power-law matrix)
+template<typename T, bool VS> __host__ __device__ constexpr int pipe_slots_of(){ return VS ? pipe_slots<T>() / VS_SLOT_DIV : pipe_slots<T>(); }
 static constexpr int PIPE_LONGROW = 2048;       // slow path: rows at least this long are reduced by the whole CTA
 static constexpr int PIPE_WARPROW = 96;         // rows at least this long are reduced by a whole warp instead of TPR lanes
 
@@ -62,7 +66,7 @@ __global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int til
 struct vsplit_view { const int *trow, *tnz, *vmap; void *part; int ntiles; };
 
 template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0, bool LPC = false, bool VS = false>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
+__global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
                                                             const T * __restrict__ vals, const T * __restrict__ x, T *y,
                                                             scalar_arg<T> alpha_s, scalar_arg<T> beta_s, const int * __restrict__ cta_tiles,
                                                             void *partials_v, unsigned int *ticket, T *dot_out, const int *skip_flag, int xpf, int cols,
@@ -70,8 +74,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                                                             int trot, int twait, vsplit_view vs){
     static_assert(!VS || (NBP == 0 && !LPC), "the virtual-row form is the plain product");
     constexpr int ROWS = THREADS / TPR;
-    constexpr int CAP  = THREADS * pipe_slots<T>();
-    constexpr int PIPE_UNR = pipe_slots<T>();              // non-zeros a stage can hold (after 4-alignment slack)
+    constexpr int CAP  = THREADS * pipe_slots_of<T, VS>();  // non-zeros a stage can hold (after 4-alignment slack)
+    constexpr int PIPE_UNR = pipe_slots_of<T, VS>();
     constexpr int PSL  = ROWS + 4;                          // ints of the pntr slice per stage
     constexpr size_t STAGE_BYTES = (size_t) (CAP + 4) * (sizeof(T) + sizeof(int)) + PSL * sizeof(int);
     static_assert(STAGE_BYTES % 16 == 0, "stage must stay 16-byte aligned");
@@ -80,8 +84,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
     constexpr int BND = 64;
     __shared__ int      bnd[BND], bnd1[BND];
     __shared__ int      brw[VS ? BND : 1], brw1[VS ? BND : 1];  // VS: first virtual row of the tile (bit 0: the tile holds long rows) / of the next tile
-    __shared__ int      vl_count, vl_row[VS ? ROWS : 1];        // VS: long rows of the current tile, dealt over ALL warps of the CTA
-    __shared__ T        vl_sum[VS ? ROWS : 1];
     __shared__ int      stage_a0[STAGES];                   // first staged non-zero index of the tile, or -1: not staged (slow path)
     __shared__ T        red[32];
 
@@ -169,6 +171,36 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
         };
         if (tid == 0) for (int k = 0; k < STAGES - 1 && k < ntile; k++) issue(k, bnd[k % BND], bnd1[k % BND]);
 
+        // VS (heavy-tailed rows): the gathers are dealt by NON-ZERO, not by row, and run one tile ahead of the sums.
+        //   gathers(k):  thread t takes entries t, t + THREADS, ... of tile k (at most pipe_slots of them): column indices from the
+        //                stage, then all operands of x in flight together — every lane of every warp carries the same number of
+        //                gathers whatever the row lengths;
+        //   products(k): when they are back, the staged values are overwritten by value * operand;            -- barrier --
+        //   gathers(k+1) are issued NOW, and stay in flight while
+        //   sums(k):     the rows of tile k are summed from the products in shared memory (TPR lanes per row in strides; rows of
+        //                PIPE_WARPROW entries and more by their warp), y is written;                           -- barrier --
+        // With rows walked by their own lanes (the general form) the longest row of a tile sets the pace: ~6 dependent gather round
+        // trips per tile on the power-law matrix (626 us; cuSPARSE's merge-based csrmv_v3: 275 us).
+        [[maybe_unused]] int vs_c[PIPE_UNR];
+        [[maybe_unused]] T vs_x[PIPE_UNR];
+        [[maybe_unused]] int vs_off = 0, vs_nz = 0;
+        [[maybe_unused]] auto vs_gathers = [&](int kk){
+            const int ss = kk % STAGES;
+            mbar_wait(full + ss, (uint32_t) ((kk / STAGES) & 1));
+            const int *spn = stage_ptr(ss), *scn = stage_cols(ss);
+            const int r0n = tile_r0(kk), nr = min((brw1[kk % BND] & ~3) - r0n, rows - r0n);
+            vs_off = spn[0] - stage_a0[ss];
+            vs_nz = spn[nr] - spn[0];
+            #pragma unroll
+            for (int u = 0; u < PIPE_UNR; u++) if (tid + u * THREADS < vs_nz) vs_c[u] = scn[vs_off + tid + u * THREADS];
+            #pragma unroll
+            for (int u = 0; u < PIPE_UNR; u++) if (tid + u * THREADS < vs_nz) vs_x[u] = (xpf & 2) ? one_of<T>() : ld_ro(x + vs_c[u]);   // xpf: probe bits (HB_VS_PROBE)
+        };
+        if constexpr (VS){
+            __syncthreads();                                    // stage_a0 of the first tiles, written by thread 0 above
+            vs_gathers(0);
+        }
+
         for (int k = 0; k < ntile; k++){
             const int s = k % STAGES;
             if (tid == 0 && k + STAGES - 1 < ntile) issue(k + STAGES - 1, bnd[(k + STAGES - 1) % BND], bnd1[(k + STAGES - 1) % BND]);
@@ -189,17 +221,66 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                 __syncthreads();
                 halo_pending = false;
             }
+            if constexpr (VS){
+                T *sv = stage_vals(s);
+                #pragma unroll
+                for (int u = 0; u < PIPE_UNR; u++)              // products(k): waits for the gathers issued one tile ago
+                    if (tid + u * THREADS < vs_nz) sv[vs_off + tid + u * THREADS] = hmul(sv[vs_off + tid + u * THREADS], vs_x[u]);
+                fence_proxy_async();                            // generic-proxy writes into a stage that a bulk copy refills later
+                __syncthreads();
+                const int r0 = tile_r0(k), myrow = r0 + grp;
+                const int *sp = stage_ptr(s);
+                const int a0 = stage_a0[s];
+                const bool live_row = grp < (brw1[k % BND] & ~3) - r0 && myrow < rows;
+                int rs = 0, re = 0, vdst = 0;
+                if (live_row){ rs = sp[grp]; re = sp[grp + 1]; if (sub == 0) vdst = __ldg(vs.vmap + myrow); }
+                if (k + 1 < ntile) vs_gathers(k + 1);           // in flight during the sums below and the barrier
+                T sum = zero_of<T>();
+                const int end = re - a0;
+                const bool wlong = (re - rs) >= PIPE_WARPROW;
+                if (!wlong && !(xpf & 1)){
+                    T sum2 = zero_of<T>();
+                    int j = rs + sub - a0;
+                    for (; j + TPR < end; j += 2 * TPR){ sum = hadd(sum, sv[j]); sum2 = hadd(sum2, sv[j + TPR]); }
+                    if (j < end) sum = hadd(sum, sv[j]);
+                    sum = hadd(sum, sum2);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, wlong && sub == 0 && !(xpf & 1));
+                while (todo){                                   // long rows: by their warp, from the products (no gathers here)
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int ls = __shfl_sync(0xffffffffu, rs, src) - a0, le = __shfl_sync(0xffffffffu, re, src) - a0;
+                    T part = zero_of<T>(), part2 = zero_of<T>();
+                    int j = ls + (tid & 31);
+                    for (; j + 32 < le; j += 64){ part = hadd(part, sv[j]); part2 = hadd(part2, sv[j + 32]); }
+                    if (j < le) part = hadd(part, sv[j]);
+                    part = shfl_from(warp_sum(hadd(part, part2)), 0);
+                    if ((tid & 31) == src) sum = part;
+                }
+                #pragma unroll
+                for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
+                if (sub == 0 && live_row){
+                    if (vdst < 0){
+                        reinterpret_cast<T*>(vs.part)[~vdst] = sum;    // a segment: raw partial sum, combined afterwards
+                    }else if (DOT){
+                        y[vdst] = sum;
+                        dot_acc = hfma(hconj(ld_ro(x + vdst)), sum, dot_acc);
+                    }else{
+                        T out = hmul(alpha, sum);
+                        if (use_beta) out = hfma(beta, y[vdst], out);
+                        y[vdst] = out;
+                    }
+                }
+                __syncthreads();                                // stage s may be refilled
+                continue;
+            }
             mbar_wait(full + s, (uint32_t) ((k / STAGES) & 1));
             const int r0 = tile_r0(k);
             const int myrow = r0 + grp;
             const int *sp = stage_ptr(s);
             const int a0 = stage_a0[s];
             int rs = 0, re = 0;
-            bool live_row = myrow < rows;
-            if constexpr (VS) live_row = grp < (brw1[k % BND] & ~3) - r0 && myrow < rows;
-            const bool tile_has_long = VS && (brw[k % BND] & 1);  // block-uniform, from the tile table
-            int vdst = 0;                                       // VS: where this virtual row's sum goes (loaded early, used after the sweep)
-            if constexpr (VS){ if (live_row && sub == 0) vdst = __ldg(vs.vmap + myrow); }
+            const bool live_row = myrow < rows;
             if (live_row){ rs = sp[grp]; re = sp[grp + 1]; }
             T sum = zero_of<T>();
             if constexpr (NBP > 0 && LPC){
@@ -315,34 +396,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
                     }
                 }
                 sum = hadd(sum, sum2);
-                // VS: a tile made of long segments has only a handful of rows, all owned by the first lanes of warp 0 — deal the long
-                // rows of the tile over all warps of the CTA instead (the tile table says which tiles have any: no barrier elsewhere)
-                if (tile_has_long){
-                    if (tid == 0) vl_count = 0;
-                    __syncthreads();
-                    if (wlong && sub == 0) vl_row[atomicAdd(&vl_count, 1)] = grp;
-                    __syncthreads();
-                    const int nl = vl_count;
-                    for (int q = tid >> 5; q < nl; q += THREADS / 32){
-                        const int lr = vl_row[q], ls = sp[lr] - a0, le = sp[lr + 1] - a0;
-                        T part = zero_of<T>(), part2 = zero_of<T>();
-                        int j = ls + (tid & 31);
-                        for (; j + 96 < le; j += 128){
-                            const int c0 = sc[j], c1 = sc[j + 32], c2 = sc[j + 64], c3 = sc[j + 96];
-                            const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
-                            part = hfma(sv[j], x0, part); part2 = hfma(sv[j + 32], x1, part2);
-                            part = hfma(sv[j + 64], x2, part); part2 = hfma(sv[j + 96], x3, part2);
-                        }
-                        for (; j < le; j += 32) part = hfma(sv[j], ld_ro(x + sc[j]), part);
-                        part = warp_sum(hadd(part, part2));
-                        if ((tid & 31) == 0) vl_sum[lr] = part;
-                    }
-                    __syncthreads();
-                    if (wlong && sub == 0) sum = vl_sum[grp];
-                }
                 // warp-cooperative pass over this warp's long rows (heavy-tailed row lengths): 32 lanes stride over the row in
                 // shared memory, four entries per lane in flight, shuffle reduction; the owner lane (sub == 0) keeps the sum
-                unsigned todo = __ballot_sync(0xffffffffu, !tile_has_long && wlong && sub == 0);
+                unsigned todo = __ballot_sync(0xffffffffu, wlong && sub == 0);
                 while (todo){
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -397,20 +453,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 256 ? 3 : 6)) spmv_pipe_k
             }
             #pragma unroll
             for (int d = TPR / 2; d > 0; d >>= 1) sum = hadd(sum, shfl_down(sum, d));
-            if constexpr (VS){
-                if (sub == 0 && live_row){
-                    if (vdst < 0){
-                        reinterpret_cast<T*>(vs.part)[~vdst] = sum;    // a segment: raw partial sum, combined afterwards
-                    }else if (DOT){
-                        y[vdst] = sum;
-                        dot_acc = hfma(hconj(ld_ro(x + vdst)), sum, dot_acc);
-                    }else{
-                        T out = hmul(alpha, sum);
-                        if (use_beta) out = hfma(beta, y[vdst], out);
-                        y[vdst] = out;
-                    }
-                }
-            }else if (sub == 0 && myrow < rows){
+            if (sub == 0 && myrow < rows){
                 if (DOT){
                     y[myrow] = sum;
                     dot_acc = hfma(hconj(ld_ro(x + myrow)), sum, dot_acc);
