@@ -418,3 +418,47 @@ def test_gpu_vector_semantics(engine):
         assert np.all(f.unload() == np.array(3, dtype=dt))
     assert engine.vector(11, 2.5).unload().tolist() == [2.5] * 11
     assert engine.launch_count() > 0
+
+
+# ---- parity at scale ("iteration-count parity taken at 128^3 ... where the CPU solve completes"): counts, true residuals
+# and 256 sampled solution entries recorded from the unmodified reference (complex GMRES: the 'C'-patched build) by
+# tests/golden/make_golden.py scale -> tests/golden/ref_counts_scale.json
+def _scale_cases():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_counts_scale.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("key", sorted(_scale_cases()))
+def test_solver_parity_at_scale(engine, key):
+    ent = _scale_cases()[key]
+    parts = key.split("/")
+    solver, (gen, n), dt = parts[0], parts[1].split(":"), parts[2]
+    n = int(n)
+    if gen == "powerlaw":
+        p, i, v = mg.powerlaw(N=n, lmax=min(65536, n // 4), dtype=dt)
+        b = mg.probe_x(n, dt, seed=31).astype(np.complex128 if dt.startswith("c") else np.float64)
+        b = (b / np.linalg.norm(b)).astype(NP[dt])          # the hashed right-hand side of make_golden.hashed_rhs
+    else:
+        p, i, v = mg.GENERATORS[gen](n, dtype=dt)
+        b = mg.rhs(p.size - 1, dt)
+    N = p.size - 1
+    assert N == ent["rows"] and i.size == ent["nnz"]
+    gp, gi, gv = load_csr(engine, p, i, v)
+    A = hb.make_sparse_matrix(engine, N, gp, gi, gv)
+    gb, gx = engine.load(b), engine.new_vector(NP[dt])
+    if solver == "cg":
+        it, _ = hb.solve_cg(engine, 1e-8, 10 ** 6, gp, gi, gv, gb, gx, matrix=A)
+    else:
+        it, _ = hb.solve_gmres(engine, 1e-8, 10 ** 6, int(parts[3][1:]), gp, gi, gv, gb, gx, matrix=A)
+    assert abs(it - ent["iters"]) <= 2, (key, it, ent["iters"])
+    gr = engine.load(b)
+    A.gemv("N", -1.0, gx, 1.0, gr)
+    assert hb.norm2(engine, gr) < 2e-8, key                 # the reference reached 0.9 - 1.2e-8 (true residual; GMRES stops on an estimate)
+    x = gx.unload()
+    idx = np.array(ent["sample_index"])
+    xs = np.array(ent["sample_re"]) + (1j * np.array(ent["sample_im"]) if "sample_im" in ent else 0)
+    # both sides solved to ||r|| ~ 1e-8: entries agree to that over the smallest singular value, not to round-off
+    assert np.max(np.abs(x[idx] - xs)) <= 2e-5 * max(np.max(np.abs(xs)), 1e-30), key
