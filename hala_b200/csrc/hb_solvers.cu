@@ -257,7 +257,9 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
     event_pair evs;
     HB_CUDA(cudaEventCreateWithFlags(&evs.ev[0], cudaEventDisableTiming));
     HB_CUDA(cudaEventCreateWithFlags(&evs.ev[1], cudaEventDisableTiming));
-    const int batch = 8;
+    // iterations enqueued per look at the host-mapped status (HB_CG_BATCH: 1 for profiling, so that a short solve launches few no-ops)
+    static const int batch_env = [](){ const char *e = getenv("HB_CG_BATCH"); const int q = e ? atoi(e) : 0; return q >= 1 && q <= 64 ? q : 8; }();
+    const int batch = batch_env;
     long long it = 0;
     for (long long bidx = 0; ; bidx++){
         for (int j = 0; j < batch; j++, it++){

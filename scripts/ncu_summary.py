@@ -100,12 +100,13 @@ def launches(src, dst, ours=("spmv", "cg_", "dcg_", "csr_", "vec_", "reduce", "m
         a = agg.setdefault(short, [0, 0.0])
         a[0] += 1
         a[1] += v
-    tot_ours = sum(a[1] for k, a in agg.items() if any(o in k for o in ours))
+    is_ours = lambda k: any(o in k for o in ours) and not k.startswith(("at::", "at_cuda", "cub::", "thrust::", "nccl"))
+    tot_ours = sum(a[1] for k, a in agg.items() if is_ours(k))
     with open(dst + ".launches.csv", "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "launches", "total_us", "mean_us", "share_of_our_kernels_pct", "ours"])
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            mine = any(o in k for o in ours)
+            mine = is_ours(k)
             w.writerow([k, a[0], f"{a[1]:.1f}", f"{a[1] / a[0]:.2f}", f"{100 * a[1] / tot_ours:.1f}" if mine and tot_ours else "", int(mine)])
     print("wrote", dst + ".launches.csv")
 
