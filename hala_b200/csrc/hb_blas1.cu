@@ -179,6 +179,8 @@ int hb_copy(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *y, int
     HB_ARG(ctx, "ctx is null");
     if (n <= 0) return HB_OK;
     HB_ARG(x && y, "null vector");
+    HB_ARG(incx != 0 && incy != 0, "zero increment");
+    x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype));
     HB_DISPATCH(dtype, {
         if (incx == 1 && incy == 1 && aligned16(x) && aligned16(y) && (size_t) n >= vec16<T>::N){
             size_t nvec = (size_t) n / vec16<T>::N;
@@ -203,6 +205,8 @@ int hb_axpy(hb_ctx *ctx, int dtype, int n, const void *alpha, const void *x, int
     HB_ARG(ctx && alpha, "null");
     if (n <= 0) return HB_OK;
     HB_ARG(x && y, "null vector");
+    HB_ARG(incx != 0 && incy != 0, "zero increment");
+    x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype));
     HB_DISPATCH(dtype, {
         scalar_arg<T> a = make_scalar<T>(ctx, alpha);
         if (incx == 1 && incy == 1 && aligned16(x) && aligned16(y) && (size_t) n >= vec16<T>::N){
@@ -226,7 +230,7 @@ int hb_axpy(hb_ctx *ctx, int dtype, int n, const void *alpha, const void *x, int
 
 int hb_scal(hb_ctx *ctx, int dtype, int n, const void *alpha, void *x, int incx){
     HB_ARG(ctx && alpha, "null");
-    if (n <= 0) return HB_OK;
+    if (n <= 0 || incx <= 0) return HB_OK;                 // netlib ?scal: nothing to do for a non-positive increment
     HB_ARG(x, "null vector");
     HB_DISPATCH(dtype, {
         scalar_arg<T> a = make_scalar<T>(ctx, alpha);
@@ -252,6 +256,8 @@ int hb_scal(hb_ctx *ctx, int dtype, int n, const void *alpha, void *x, int incx)
 int hb_dot(hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, const void *y, int incy, void *result){
     HB_ARG(ctx && result, "null");
     HB_ARG(n <= 0 || (x && y), "null vector");
+    HB_ARG(n <= 0 || (incx != 0 && incy != 0), "zero increment");
+    if (n > 0){ x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype)); }
     HB_DISPATCH(dtype, {
         if (conj && is_cplx<T>::value) return launch_reduce<1, T>(ctx, n, (const T*) x, incx, (const T*) y, incy, result);
         return launch_reduce<0, T>(ctx, n, (const T*) x, incx, (const T*) y, incy, result);
@@ -262,6 +268,7 @@ int hb_dot(hb_ctx *ctx, int dtype, int conj, int n, const void *x, int incx, con
 int hb_asum(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result){
     HB_ARG(ctx && result, "null");
     HB_ARG(n <= 0 || x, "null vector");
+    if (incx <= 0) n = 0;                                   // netlib ?asum: zero for a non-positive increment
     HB_DISPATCH(dtype, { return launch_reduce<3, T>(ctx, n, (const T*) x, incx, (const T*) x, incx, result); });
     return HB_OK;
 }
@@ -269,6 +276,7 @@ int hb_asum(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result
 int hb_nrm2(hb_ctx *ctx, int dtype, int n, const void *x, int incx, void *result){
     HB_ARG(ctx && result, "null");
     HB_ARG(n <= 0 || x, "null vector");
+    if (incx <= 0) n = 0;                                   // netlib ?nrm2: zero for a non-positive increment
     HB_DISPATCH(dtype, { return launch_reduce<2, T>(ctx, n, (const T*) x, incx, (const T*) x, incx, result); });
     return HB_OK;
 }

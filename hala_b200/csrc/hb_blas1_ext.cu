@@ -202,6 +202,8 @@ int hb_swap(hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy)
     HB_ARG(ctx, "ctx is null");
     if (n <= 0) return HB_OK;
     HB_ARG(x && y, "null vector");
+    HB_ARG(incx != 0 && incy != 0, "zero increment");
+    x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype));
     const bool vec = incx == 1 && incy == 1 && aligned16(x) && aligned16(y);
     HB_DISPATCH(dtype, {
         if (vec) swap_kernel<T, true><<<x_grid(ctx, n, X_THREADS * 8), X_THREADS, 0, ctx->stream>>>(n, (T*) x, 1, (T*) y, 1);
@@ -234,6 +236,8 @@ int hb_rot(hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy, 
     HB_ARG(ctx && c && s, "null");
     if (n <= 0) return HB_OK;
     HB_ARG(x && y, "null vector");
+    HB_ARG(incx != 0 && incy != 0, "zero increment");
+    x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype));
     const bool vec = incx == 1 && incy == 1 && aligned16(x) && aligned16(y);
     HB_DISPATCH(dtype, {
         rot_args<T> a;
@@ -254,6 +258,8 @@ int hb_rotm(hb_ctx *ctx, int dtype, int n, void *x, int incx, void *y, int incy,
     HB_ARG(dtype == HB_F32 || dtype == HB_F64, "rotm is defined for real types only");
     if (n <= 0) return HB_OK;
     HB_ARG(x && y, "null vector");
+    HB_ARG(incx != 0 && incy != 0, "zero increment");
+    x = hb_blas_base(x, n, incx, hb_dtype_size(dtype)); y = hb_blas_base(y, n, incy, hb_dtype_size(dtype));
     if (dtype == HB_F32){
         rotm_args<float> a; a.dev = nullptr;
         if (ctx->pointer_mode == HB_POINTER_HOST) memcpy(a.p, param, sizeof(a.p)); else a.dev = (const float*) param;

@@ -307,6 +307,13 @@ struct per_device_flag {
 };
 
 
+// BLAS increments: a negative increment walks the vector backwards from element (n-1)*|inc| (netlib: IX = (1-N)*INCX + 1), so the
+// kernels, which index base[i * inc] with a signed product, get the base moved to that element; a zero increment is an argument error.
+static inline const void* hb_blas_base(const void *p, int n, int inc, size_t es){
+    return inc < 0 ? (const void*) ((const char*) p + (size_t) ((long long) (1 - n) * (long long) inc) * es) : p;
+}
+static inline void* hb_blas_base(void *p, int n, int inc, size_t es){ return const_cast<void*>(hb_blas_base((const void*) p, n, inc, es)); }
+
 // dtype dispatch on the host
 #define HB_DISPATCH(dtype, ...) \
     switch (dtype) { \

@@ -719,6 +719,7 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
     HB_ARG(rows == 0 || pntr, "pntr is null");
     HB_ARG(nnz == 0 || (indx && vals), "indx/vals null");
     hb_csr *A = new hb_csr();
+    struct csr_guard { hb_csr *a; ~csr_guard(){ if (a) hb_csr_destroy(a); } } guard{A};       // every early return below frees the object and its tables
     A->ctx = ctx; A->dtype = dtype; A->rows = rows; A->cols = cols; A->nnz = nnz;
     A->pntr = pntr; A->indx = indx; A->vals = vals;
     A->vec_aligned = aligned16p(indx) && aligned16p(vals);
@@ -777,9 +778,10 @@ int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int
         const char *vse = getenv("HB_VSPLIT");
         if (heavy_tail && hb_spmv_variant(A) == 3 && !(vse && vse[0] == '0')){
             int rc = vsplit_build(ctx, A);
-            if (rc != HB_OK){ hb_csr_destroy(A); return rc; }
+            if (rc != HB_OK) return rc;
         }
     }
+    guard.a = nullptr;
     *out = A;
     return HB_OK;
 }

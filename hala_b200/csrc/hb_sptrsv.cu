@@ -327,6 +327,8 @@ int tri_grid(hb_ctx *ctx){ return ctx->num_sms * 4; }
 // levels + level-ordered row list of op 'N' for the given structure
 int analyse_levels(hb_ctx *ctx, int n, bool lower, const int *pntr, const int *indx, unsigned int *ticket, int **order_out, int *nlevels_out){
     int *level = nullptr, *hist = nullptr, *order = nullptr, *maxl = nullptr;
+    struct temporaries { int **a, **b, **c, **d; bool keep_d = false;     // freed on every exit; `order` survives a successful one
+        ~temporaries(){ cudaFree(*a); cudaFree(*b); cudaFree(*c); if (!keep_d) cudaFree(*d); } } tmp{&level, &hist, &maxl, &order};
     HB_CUDA(cudaMalloc((void**) &level, sizeof(int) * (size_t) (n + 1)));
     HB_CUDA(cudaMalloc((void**) &maxl, sizeof(int)));
     HB_CUDA(cudaMemsetAsync(level, 0xff, sizeof(int) * (size_t) (n + 1), ctx->stream));
@@ -349,7 +351,7 @@ int analyse_levels(hb_ctx *ctx, int n, bool lower, const int *pntr, const int *i
     tri_fill_kernel<<<g, 256, 0, ctx->stream>>>(n, level, hist, order);
     HB_LAUNCH_CHECK(ctx);
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(level); cudaFree(hist); cudaFree(maxl);
+    tmp.keep_d = true;
     *order_out = order; *nlevels_out = nlev;
     return HB_OK;
 }
@@ -478,6 +480,7 @@ int hb_ilu0(hb_ctx *ctx, int dtype, int rows, int nnz, const int *pntr, const in
     if (ilu != vals) HB_CUDA(cudaMemcpyAsync(ilu, vals, es * (size_t) nnz, cudaMemcpyDeviceToDevice, ctx->stream));
     int *diag = nullptr, *flags = nullptr, *order = nullptr;
     unsigned int *ticket = nullptr;
+    struct temporaries { int **a, **b, **c; unsigned int **d; ~temporaries(){ cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*d); } } tmp{&diag, &flags, &order, &ticket};
     HB_CUDA(cudaMalloc((void**) &diag, sizeof(int) * (size_t) rows));
     HB_CUDA(cudaMalloc((void**) &flags, sizeof(int) * ((size_t) rows + 2)));      // [0] bad-row marker, [1..] done flags
     HB_CUDA(cudaMalloc((void**) &ticket, sizeof(unsigned int)));
@@ -504,7 +507,6 @@ int hb_ilu0(hb_ctx *ctx, int dtype, int rows, int nnz, const int *pntr, const in
         }
         if (e != cudaSuccess) rc = hb_cuda_fail(e, "hb_ilu0");
     }
-    cudaFree(diag); cudaFree(flags); cudaFree(ticket); cudaFree(order);
     return rc;
 }
 

@@ -157,15 +157,22 @@ __global__ void __launch_bounds__(TR_THREADS) tr_rows_kernel(int nnz, int rows, 
 }
 
 // ------------------------------------------------------------------------------------------------ per product: fingerprint, gather
-// 64-bit fingerprint of an array of 32-bit words: sum of word * key(position) modulo 2^64, keys odd and derived from a mixed
-// packet index, so any single-word change always changes the sum and unrelated changes cancel with probability ~2^-64.
+// 64-bit fingerprint of an array of 32-bit words: sum of word * key(position) modulo 2^64 with 64-bit ODD keys derived from a mixed
+// packet index.  A change confined to one word always changes the sum (odd key, word delta < 2^32); a change of several words
+// (one double already is two) is missed only when sum delta_i * key_i == 0 mod 2^64, about 2^-64 per update for keys that behave as
+// random (with the 32-bit keys of round 1 that was 2^-32).  The keys are public: a caller who needs certainty rather than odds uses
+// HB_TRANS_FROZEN + hb_csr_values_changed or HB_TRANS_SCATTER.
 // Integer addition is associative: the block partials are added with one atomic per block and the result is still deterministic.
-__device__ __forceinline__ unsigned int tr_mix(unsigned long long packet){
-    unsigned int x = (unsigned int) packet * 0x9E3779B1u + (unsigned int) (packet >> 32) * 0x85EBCA77u;
-    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
-    return x;
+__device__ __forceinline__ unsigned long long tr_mix(unsigned long long packet){
+    unsigned long long z = packet + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
 }
-__device__ __forceinline__ unsigned int tr_key(unsigned int base, int w){ return __funnelshift_l(base, base, 7 * w + 1) | 1u; }
+__device__ __forceinline__ unsigned long long tr_key(unsigned long long base, int w){
+    const int r = 13 * w + 1;
+    return ((base << r) | (base >> (64 - r))) | 1ull;
+}
 
 template<bool VEC>
 __global__ void __launch_bounds__(TR_THREADS) tr_fingerprint_kernel(size_t nwords, const unsigned int * __restrict__ w, unsigned long long *out){
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(TR_THREADS) tr_fingerprint_kernel(size_t nword
     stream_sweep<unsigned int, VEC, 4>(nwords,
         [&](int u, size_t p){ pk[u] = __ldcs(reinterpret_cast<const uint4*>(w) + p); },
         [&](int u, size_t p){
-            const unsigned int b = tr_mix(p);
+            const unsigned long long b = tr_mix(p);
             h += (unsigned long long) pk[u].x * tr_key(b, 0);
             h += (unsigned long long) pk[u].y * tr_key(b, 1);
             h += (unsigned long long) pk[u].z * tr_key(b, 2);

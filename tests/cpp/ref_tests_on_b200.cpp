@@ -186,6 +186,44 @@ template<typename T> void fused_front_doors(){
     hassert(testvec(yig, yic, 1.E+6 * hala::norm2(yic)));
 }
 
+// Row f3, staging half: page-locked containers through load / unload / gpu_bind_vector and a mixed_engine solve.
+template<typename T> void pinned_containers(){
+    current_test<T> tests("pinned load/unload");
+    using P = typename hala::define_standard_precision<T>::value_type;
+    const int n = 32, N = n * n;
+    std::vector<int> pntr, indx; std::vector<T> vals;
+    lap2d<T>(n, pntr, indx, vals);
+    hala::pinned_vector<int> ppntr(pntr.begin(), pntr.end()), pindx(indx.begin(), indx.end());
+    hala::pinned_vector<T> pvals(vals.begin(), vals.end()), pb(N, hala::get_cast<T>(1.0 / n)), px, pback;
+    hala::gpu_engine egpu(0);
+    hala::mixed_engine emix(egpu);
+    auto gv = egpu.load(pvals);                      // load from pinned memory, unload into a pinned container
+    gv.unload(pback);
+    hassert(pback.size() == pvals.size());
+    bool same = true;
+    for(size_t i=0; i<pvals.size(); i++) same = same && (pback[i] == pvals[i]);
+    hassert(same);
+    {   // gpu_bind_vector on a pinned container: loaded on construction, written back on destruction
+        hala::pinned_vector<T> y(N, hala::get_cast<T>(2.0));
+        {
+            auto by = hala::gpu_bind_vector(egpu, y);
+            hala::scal(egpu, 0.5, by);
+        }
+        bool halved = true;
+        for(auto const &v : y) halved = halved && (std::abs(v - hala::get_cast<T>(1.0)) < 1.E-6);
+        hassert(halved);
+    }
+    std::vector<T> b(N, hala::get_cast<T>(1.0 / n)), xref;
+    const P tol = std::is_same<P, float>::value ? 1.E-4f : 1.E-9;
+    int it_ref = hala::solve_cg(emix, hala::stop_criteria<P>(tol, 1000), pntr, indx, vals,
+                                [&](auto const &in, auto &out)->void{ hala::vcopy(egpu, in, out); }, b, xref);
+    int it_pin = hala::solve_cg(emix, hala::stop_criteria<P>(tol, 1000), ppntr, pindx, pvals,
+                                [&](auto const &in, auto &out)->void{ hala::vcopy(egpu, in, out); }, pb, px);
+    hassert(it_ref == it_pin);
+    std::vector<T> xpin(px.begin(), px.end());
+    hassert(testvec(xpin, xref, hala::norm2(xref)));
+}
+
 // Row f3 through the header layer: a gpu_sparse_matrix kept across products, op 'T' / 'C' on the cached transpose in its three modes,
 // values rewritten in place between products (the view is non-owning, reference gpu/hala_cuda_sparse_general.hpp:186-190), against
 // hala::sparse_gemv on the CPU engine.
@@ -280,6 +318,7 @@ int main(int argc, char**){
     begin_report(std::string("reference solver templates on gpu_engine / mixed_engine"));
     perform([]()->void{ solvers_on_engines<float>(); solvers_on_engines<double>(); solvers_on_engines<std::complex<float>>(); solvers_on_engines<std::complex<double>>(); });
     perform([]()->void{ fused_front_doors<float>(); fused_front_doors<double>(); fused_front_doors<std::complex<float>>(); fused_front_doors<std::complex<double>>(); });
+    perform([]()->void{ pinned_containers<float>(); pinned_containers<double>(); pinned_containers<std::complex<float>>(); pinned_containers<std::complex<double>>(); });
 
     end_report(name);
     return test_result();

@@ -462,3 +462,44 @@ def test_solver_parity_at_scale(engine, key):
     xs = np.array(ent["sample_re"]) + (1j * np.array(ent["sample_im"]) if "sample_im" in ent else 0)
     # both sides solved to ||r|| ~ 1e-8: entries agree to that over the smallest singular value, not to round-off
     assert np.max(np.abs(x[idx] - xs)) <= 2e-5 * max(np.max(np.abs(xs)), 1e-30), key
+
+
+def test_blas1_negative_and_zero_increments(engine):
+    """netlib / cuBLAS semantics the reference inherits (blas/hala_blas_1.hpp passes increments through): a negative increment walks
+    the vector backwards from element (n-1)*|inc|; single-vector operations do nothing (return zero) for a non-positive increment;
+    a zero increment of a two-vector operation is an argument error, not a read before the base pointer."""
+    import ctypes as C
+    from hala_b200.capi import lib
+    n = 1000
+    x = mg.probe_x(3 * n, "f64", seed=41)
+    y = mg.probe_x(3 * n, "f64", seed=42)
+    gx, gy = engine.load(x), engine.load(y)
+    a = np.array([1.5])
+    ap = a.ctypes.data_as(C.c_void_p)
+    for incx, incy in ((-1, 1), (2, -3), (-2, -1)):
+        xs = x[:1 + (n - 1) * abs(incx):abs(incx)][::(1 if incx > 0 else -1)]
+        ys = slice(0, 1 + (n - 1) * abs(incy), abs(incy))
+        # axpy
+        gy.load(y)
+        assert lib.hb_axpy(engine.ctx, 1, n, ap, gx.ptr, incx, gy.ptr, incy) == 0
+        want = y.copy()
+        yv = want[ys][::(1 if incy > 0 else -1)] + 1.5 * xs
+        want[ys] = yv[::(1 if incy > 0 else -1)]
+        np.testing.assert_allclose(gy.unload(), want, rtol=1e-15, atol=0)
+        # dot (result through the host pointer mode)
+        r = np.zeros(1)
+        gy.load(y)
+        assert lib.hb_dot(engine.ctx, 1, 1, n, gx.ptr, incx, gy.ptr, incy, r.ctypes.data_as(C.c_void_p)) == 0
+        ref = float(np.dot(xs, y[ys][::(1 if incy > 0 else -1)]))
+        assert abs(r[0] - ref) <= 1e-12 * np.sum(np.abs(xs * y[ys][::(1 if incy > 0 else -1)]))
+        # copy
+        assert lib.hb_copy(engine.ctx, 1, n, gx.ptr, incx, gy.ptr, incy) == 0
+        want = y.copy()
+        want[ys] = xs[::(1 if incy > 0 else -1)]
+        np.testing.assert_array_equal(gy.unload(), want)
+    assert lib.hb_axpy(engine.ctx, 1, n, ap, gx.ptr, 0, gy.ptr, 1) == 2         # HB_ERR_ARG
+    r = np.full(1, 7.0)
+    assert lib.hb_nrm2(engine.ctx, 1, n, gx.ptr, -1, r.ctypes.data_as(C.c_void_p)) == 0 and r[0] == 0.0
+    gy.load(y)
+    assert lib.hb_scal(engine.ctx, 1, n, ap, gy.ptr, -1) == 0
+    np.testing.assert_array_equal(gy.unload(), y)
