@@ -282,11 +282,6 @@ __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) 
             int rs = 0, re = 0;
             const bool live_row = myrow < rows;
             if (live_row){ rs = sp[grp]; re = sp[grp + 1]; }
-            // fused <x,y>: x[row] is asked for NOW, with the gathers, not after the row's last FMA where its latency would sit at the
-            // end of every tile in front of the barrier (7-point 256^3: the fused form ran 277 us against 262 us for the plain product)
-            [[maybe_unused]] T xrow = zero_of<T>();
-            constexpr bool XROW_EARLY = DOT && sizeof(T) <= 8;   // (complex<double>: two more registers spill, the load stays late)
-            if constexpr (XROW_EARLY){ if (sub == 0 && live_row) xrow = ld_ro(x + myrow); }
             T sum = zero_of<T>();
             if constexpr (NBP > 0 && LPC){
                 constexpr int GROUPS = THREADS / NBP, RPG = ROWS / GROUPS, MU = (sizeof(T) == 16 ? 4 : 8);
@@ -461,8 +456,7 @@ __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) 
             if (sub == 0 && myrow < rows){
                 if (DOT){
                     y[myrow] = sum;
-                    if constexpr (!XROW_EARLY) xrow = ld_ro(x + myrow);
-                    dot_acc = hfma(hconj(xrow), sum, dot_acc);
+                    dot_acc = hfma(hconj(ld_ro(x + myrow)), sum, dot_acc);     // (asking for x[row] earlier, with the gathers, was measured: 3 % slower)
                 }else{
                     T out = hmul(alpha, sum);
                     if (use_beta) out = hfma(beta, y[myrow], out);

@@ -97,17 +97,21 @@ def launches(src, dst, ours=("spmv", "cg_", "dcg_", "csr_", "vec_", "reduce", "m
         v = float(r[vi].replace(",", "")) * {"ms": 1e3, "ns": 1e-3, "us": 1.0, "s": 1e6, "second": 1e6}.get(r[ui], 1.0)
         name = r[ki]
         short = name.split("(")[0].replace("void ", "")[:80]
-        a = agg.setdefault(short, [0, 0.0])
+        a = agg.setdefault(short, [0, 0.0, 0, 0.0])
         a[0] += 1
         a[1] += v
+        if v >= 10.0:                                 # launches that did work (iterations past the stop return at once: ~4 us)
+            a[2] += 1
+            a[3] += v
     is_ours = lambda k: any(o in k for o in ours) and not k.startswith(("at::", "at_cuda", "cub::", "thrust::", "nccl"))
     tot_ours = sum(a[1] for k, a in agg.items() if is_ours(k))
     with open(dst + ".launches.csv", "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["kernel", "launches", "total_us", "mean_us", "share_of_our_kernels_pct", "ours"])
+        w.writerow(["kernel", "launches", "total_us", "mean_us", "share_of_our_kernels_pct", "ours", "launches_over_10us", "mean_us_over_10us"])
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             mine = is_ours(k)
-            w.writerow([k, a[0], f"{a[1]:.1f}", f"{a[1] / a[0]:.2f}", f"{100 * a[1] / tot_ours:.1f}" if mine and tot_ours else "", int(mine)])
+            w.writerow([k, a[0], f"{a[1]:.1f}", f"{a[1] / a[0]:.2f}", f"{100 * a[1] / tot_ours:.1f}" if mine and tot_ours else "", int(mine),
+                        a[2], f"{a[3] / a[2]:.2f}" if a[2] else ""])
     print("wrote", dst + ".launches.csv")
 
 
