@@ -479,7 +479,10 @@ static int vsplit_occupancy_any(int dtype, int tpr){
     return 0;
 }
 // measurement probe (results are WRONG with it on): bit 0 skips the row sums, bit 1 replaces the gathers of x by a constant
-static int vs_probe_bits(){ const char *e = getenv("HB_VS_PROBE"); return e ? atoi(e) & 3 : 0; }
+static int vs_probe_bits(){
+    const char *e = getenv("HB_VS_PROBE"), *w = getenv("HB_VS_WARPROW");      // HB_VS_WARPROW: threshold of the warp-summed rows (probe)
+    return (e ? atoi(e) & 3 : 0) | (w ? (atoi(w) & 0xffff) << 8 : 0);
+}
 template<typename T, int TPR, bool DOT>
 static int launch_pipe_vs_tpr(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar_arg<T> alpha, scalar_arg<T> beta, T *dot_out, const int *skip){
     const hb_vsplit *v = A->vs;

@@ -64,6 +64,7 @@ __global__ void csr_partition_kernel(int rows, int nnz, const int *pntr, int til
 // to y[vs.vmap[v]]; a segment stores its raw partial sum to vs.part[~vs.vmap[v]], and vsplit_combine_kernel adds the segments of each
 // split row in order afterwards (deterministic; no atomics).
 struct vsplit_view { const int *trow, *tnz, *vmap; void *part; int ntiles; };
+static constexpr int VS_WARPROW = 96;           // VS: rows of this many entries and more are summed by their whole warp (16 / 24 / 32 / 48 measured: slower)
 
 template<typename T, int THREADS, int TPR, int STAGES, bool DOT, int NBP = 0, bool LPC = false, bool VS = false>
 __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) spmv_pipe_kernel(int rows, int nnz, const int * __restrict__ pntr, const int * __restrict__ indx,
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) 
     // virtual position `twait` (the first tile of the rotated order that touches a ghost): interior rows run while the halo is
     // still in flight, CTAs that own no boundary tile never wait.  trot = twait = 0 is a wait before the first gather.
     bool halo_pending = DOT && (pv != nullptr);
+    [[maybe_unused]] const int vs_warprow = (xpf >> 8) > 0 ? (xpf >> 8) : VS_WARPROW;       // VS only; bits 8.. of xpf: probe override
 
     const int tid = threadIdx.x, sub = tid % TPR, grp = tid / TPR;
     const T alpha = get_scalar(alpha_s), beta = get_scalar(beta_s);
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) 
                 if (k + 1 < ntile) vs_gathers(k + 1);           // in flight during the sums below and the barrier
                 T sum = zero_of<T>();
                 const int end = re - a0;
-                const bool wlong = (re - rs) >= PIPE_WARPROW;
+                const bool wlong = (re - rs) >= vs_warprow;     // summing products is a chain of LDS + add: a warp takes over early
                 if (!wlong && !(xpf & 1)){
                     T sum2 = zero_of<T>();
                     int j = rs + sub - a0;

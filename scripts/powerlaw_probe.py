@@ -38,9 +38,11 @@ for dt in DTYPES:
     scale = np.array([np.sum(np.abs(v[p[r]:p[r + 1]]) * np.abs(xh[i[p[r]:p[r + 1]]])) for r in rows])
     for tag, env in (("vsplit round-robin", {}), ("vsplit round-robin, 2 lanes per row", {"HB_VS_TPR": "2"}), ("vsplit contiguous", {"HB_PIPE_MAP": "c"}),
                      ("general kernel (HB_VSPLIT=0)", {"HB_VSPLIT": "0"}),
+                     ("vsplit, warp rows from 16", {"HB_VS_WARPROW": "16"}), ("vsplit, warp rows from 24", {"HB_VS_WARPROW": "24"}),
+                     ("vsplit, warp rows from 48", {"HB_VS_WARPROW": "48"}), ("vsplit, warp rows from 96", {"HB_VS_WARPROW": "96"}),
                      ("PROBE no row sums (wrong results)", {"HB_VS_PROBE": "1"}), ("PROBE no gathers (wrong results)", {"HB_VS_PROBE": "2"}),
                      ("PROBE neither (wrong results)", {"HB_VS_PROBE": "3"})):
-        for k in ("HB_PIPE_MAP", "HB_VSPLIT", "HB_VS_TPR", "HB_VS_PROBE"):
+        for k in ("HB_PIPE_MAP", "HB_VSPLIT", "HB_VS_TPR", "HB_VS_PROBE", "HB_VS_WARPROW"):
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.perf_counter()
@@ -60,7 +62,7 @@ for dt in DTYPES:
         emit(op="spmv", config=f"powerlaw 2^{LOG2N} {dt}", variant=tag, nnz=int(i.size), max_row=int(lens.max()), us=us, gbs=B / us / 1e3,
              frac_measured_peak=B / us / 1e3 / PEAK, create_ms=create_ms, worst_scaled_err=err, worst_scaled_err_alpha_beta=err2)
         del A
-    for k in ("HB_PIPE_MAP", "HB_VSPLIT", "HB_VS_TPR", "HB_VS_PROBE"):
+    for k in ("HB_PIPE_MAP", "HB_VSPLIT", "HB_VS_TPR", "HB_VS_PROBE", "HB_VS_WARPROW"):
         os.environ.pop(k, None)
     if refgpu is not None:
         code = 3 if dt == "c64" else 1
