@@ -137,7 +137,7 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
     void *arena = nullptr;
     // with a preconditioner the operator's output (ta) and the preconditioned vector (t = P^-1 ta) are two arrays; without, one
     const size_t nvec = (size_t) restart + 2 + (precon.fn ? 1 : 0);
-    if ((rc = hb_ctx_workspace(ctx, vec_bytes * nvec + 256 + sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
+    if ((rc = hb_ctx_workspace(ctx, vec_bytes * nvec + 256 + 2 * sizeof(T) * (size_t) (restart + 2), &arena)) != HB_OK) return rc;
     T *t = (T*) arena, *W = (T*) ((char*) arena + vec_bytes);
     T *xext = (T*) ((char*) arena + vec_bytes * ((size_t) restart + 1));
     T *ta = precon.fn ? (T*) ((char*) arena + vec_bytes * ((size_t) restart + 2)) : t;
@@ -146,7 +146,11 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
     auto halo = [&](T *v)->int{ return dist ? hb_dist_halo_exchange(dist, A->dtype, v) : HB_OK; };
     auto allsum = [&](T *v, int count)->int{ return dist ? hb_dist_allreduce_sum(dist, A->dtype, v, count) : HB_OK; };
     T *hhost = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->hscalars) + 1024);   // pinned staging, (restart+2) scalars <= 3 KiB
-    HB_ARG((size_t) (restart + 2) * sizeof(T) <= HB_SCALAR_BYTES - 1024, "restart too large for the pinned staging area (max 190)");
+    HB_ARG(2 * (size_t) (restart + 2) * sizeof(T) <= HB_SCALAR_BYTES - 1024, "restart too large for the pinned staging area (max 94)");
+    event_pair evs;
+    HB_CUDA(cudaEventCreateWithFlags(&evs.ev[0], cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&evs.ev[1], cudaEventDisableTiming));
+    static const bool pipelined = [](){ const char *e = getenv("HB_GMRES_PIPELINE"); return !(e && e[0] == '0'); }();   // 0: enqueue after the host step (A/B)
     const int saved_mode = ctx->pointer_mode;
     ctx->pointer_mode = HB_POINTER_HOST;
     struct restore { hb_ctx *c; int m; ~restore(){ c->pointer_mode = m; } } restore_mode{ctx, saved_mode};
@@ -179,22 +183,38 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
         inner_res = (R) std::sqrt((double) hreal(hhost[0]));
         Z.push_back(from_real<T>(inner_res));
 
+        // The inner iterations run one ahead of the host: the device work of iteration j + 1 (which needs nothing from the host — the
+        // Gram-Schmidt coefficients and the norm stay on the device, and so does the scale of the next basis column) is enqueued BEFORE
+        // the host waits for the k + 1 scalars of iteration j, so the Givens step of j and the launch latency of j + 1 hide behind
+        // kernels instead of leaving the GPU idle once per iteration.  The scalars travel through two device / pinned slots.  When
+        // iteration j turns out to be the last, the work enqueued for j + 1 is discarded (it touched t and basis column j + 2 only).
+        auto enqueue = [&](int j)->int{
+            T *wj = W + (size_t) j * ldw, *hd = hdev + (size_t) (j & 1) * (size_t) (restart + 2), *hh = hhost + (size_t) (j & 1) * (size_t) (restart + 2);
+            int rc2;
+            if ((rc2 = halo(wj)) != HB_OK) return rc2;
+            if ((rc2 = hb_spmv_internal(ctx, A, wj, ta, nullptr)) != HB_OK) return rc2;                      // t = A w_j ; r = P^-1 t
+            if (precon.fn && (rc2 = precon(ta, t)) != HB_OK) return rc2;
+            const int k = j + 1;
+            if ((rc2 = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, ldw, t, hd, nullptr)) != HB_OK) return rc2;
+            if ((rc2 = allsum(hd, k)) != HB_OK) return rc2;
+            if ((rc2 = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, ldw, hd, t, hd + k, -1.0, nullptr)) != HB_OK) return rc2;
+            if ((rc2 = allsum(hd + k, 1)) != HB_OK) return rc2;
+            HB_CUDA(cudaMemcpyAsync(hh, hd, sizeof(T) * (size_t) (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            HB_CUDA(cudaEventRecord(evs.ev[j & 1], ctx->stream));
+            // normalise-and-append of the next basis column: its scale is hd[k], on the device
+            if (k < restart && (rc2 = hb_scale_copy_internal(ctx, A->dtype, n, t, hd + k, W + (size_t) k * ldw, nullptr)) != HB_OK) return rc2;
+            return HB_OK;
+        };
         int inner = 0;
+        if ((inner_res > tol) && (inner < restart)){ if ((rc = enqueue(0)) != HB_OK) return rc; }
         while ((inner_res > tol) && (inner < restart)){
-            T *wj = W + (size_t) inner * ldw;
-            if ((rc = halo(wj)) != HB_OK) return rc;
-            if ((rc = hb_spmv_internal(ctx, A, wj, ta, nullptr)) != HB_OK) return rc;                        // t = A w_j ; r = P^-1 t
-            if (precon.fn && (rc = precon(ta, t)) != HB_OK) return rc;
+            if (pipelined && inner + 1 < restart){ if ((rc = enqueue(inner + 1)) != HB_OK) return rc; }
+            HB_CUDA(cudaEventSynchronize(evs.ev[inner & 1]));
             total++;
             const int k = inner + 1;
-            if ((rc = hb_multi_dot_internal(ctx, A->dtype, cproj, n, k, W, ldw, t, hdev, nullptr)) != HB_OK) return rc;
-            if ((rc = allsum(hdev, k)) != HB_OK) return rc;
-            if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, k, W, ldw, hdev, t, hdev + k, -1.0, nullptr)) != HB_OK) return rc;
-            if ((rc = allsum(hdev + k, 1)) != HB_OK) return rc;
-            HB_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(T) * (size_t) (k + 1), cudaMemcpyDeviceToHost, ctx->stream));
-            HB_CUDA(cudaStreamSynchronize(ctx->stream));
-            coeffs.assign(hhost, hhost + k);
-            const R nrm = (R) std::sqrt((double) hreal(hhost[k]));
+            const T *hh = hhost + (size_t) (inner & 1) * (size_t) (restart + 2);
+            coeffs.assign(hh, hh + k);
+            const R nrm = (R) std::sqrt((double) hreal(hh[k]));
 
             for (int i = 0; i < inner; i++) h_rot(coeffs[i], coeffs[i + 1], C[i], S[i]);
             T isin = zero_of<T>(), beta = from_real<T>(nrm);
@@ -205,14 +225,15 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
             inner_res = habs(hmul(S.back(), Z.back()));
             inner++;
             if ((inner_res > tol) && (inner < restart)){
-                if ((rc = hb_scale_copy_internal(ctx, A->dtype, n, t, hdev + k, W + (size_t) inner * ldw, nullptr)) != HB_OK) return rc;
                 Z.push_back(zero_of<T>());
                 h_rot(Z[inner - 1], Z[inner], C.back(), S.back());
+                if (!pipelined){ if ((rc = enqueue(inner)) != HB_OK) return rc; }
             }
         }
         if (!H.empty()){
             const int nz = (int) Z.size();
             h_tpsv_unn(nz, H, Z);
+            HB_CUDA(cudaStreamSynchronize(ctx->stream));      // an iteration enqueued ahead and then discarded may still be writing its scalars into hhost
             memcpy(hhost, Z.data(), sizeof(T) * (size_t) nz);
             HB_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(T) * (size_t) nz, cudaMemcpyHostToDevice, ctx->stream));
             if ((rc = hb_multi_axpy_internal(ctx, A->dtype, n, nz, W, ldw, hdev, x, nullptr, 1.0, nullptr)) != HB_OK) return rc;
