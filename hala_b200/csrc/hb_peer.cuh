@@ -2,8 +2,8 @@
 // others' exchange buffer (CUDA IPC) and the iteration kernels talk through it directly, so a CG iteration contains no
 // collective call at all:
 //   * halo:   the kernel that PRODUCES p stores the entries its neighbours need straight into their ghost slots
-//             (remote stores over NVLink, then one release flag per pushing block); the SpMV that consumes them waits on
-//             those flags in-kernel.
+//             (remote stores over NVLink by the whole grid; the block that finishes last releases one flag per neighbour); the
+//             SpMV that consumes them waits on those flags in-kernel, in front of its first tile that references a ghost column.
 //   * scalar sums (<p,Ap>, ||r||^2): the last block of the producing kernel stores this rank's partial into a slot of every
 //             peer's mailbox; every block of the consuming kernel waits for the W slots and adds them in rank order, so all
 //             ranks (and all blocks) get the same bits — the iteration stays in lock step without a host or NCCL round trip.
@@ -11,6 +11,9 @@
 // Why two buffers suffice: rank X can only write epoch g + 2 after it consumed a value of epoch g + 1 from every peer Y, and
 // Y published that value after the kernel in which it consumed epoch g (stream order).  The first exchanges of a solve go
 // through NCCL (halo of x0, all-reduce of <r,r>), which also fences one solve from the next.
+// The epoch MUST be the same number on every rank: hb_dist.cu derives it from counts all ranks agree on (iterations executed,
+// collective calls made) and re-bases it with an all-reduce(MAX) at the start of every solve; a wait that times out poisons the
+// sums with NaN, which stops every rank, and the solve is redone over NCCL.
 #pragma once
 #include "hb_common.cuh"
 
@@ -25,7 +28,7 @@ struct peer_vslot { double v[2 * HB_PEER_VMAX]; unsigned long long seq; unsigned
 // mailbox at the start of every rank's exchange buffer
 struct peer_mailbox {
     peer_slot slot[2][2][HB_MAX_PEERS];                             // [channel][epoch parity][source rank]
-    unsigned long long halo_seq[HB_MAX_PEERS][HB_HALO_BLOCKS];      // [source rank][pushing block] = epoch + 1 of the last push
+    unsigned long long halo_seq[HB_MAX_PEERS][HB_HALO_BLOCKS];      // [source rank][0] = epoch + 1 of that rank's last completed push (slots 1.. unused)
     int error;                                                      // set when a wait timed out (peer died / mis-sequenced)
     int pad[15];
     peer_vslot vslot[2][HB_MAX_PEERS];                              // [vector-sum epoch parity][source rank]

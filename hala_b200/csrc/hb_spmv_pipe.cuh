@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, (VS ? 5 : (THREADS >= 256 ? 3 : 6))) 
                 const int end = re - a0;
                 const bool wlong = (re - rs) >= vs_warprow;     // summing products is a chain of LDS + add: a warp takes over early
                 if (!wlong && !(xpf & 1)){
-                    T sum2 = zero_of<T>();
+                    T sum2 = zero_of<T>();                      // (four reads per step before the first add: measured 2 % slower)
                     int j = rs + sub - a0;
                     for (; j + TPR < end; j += 2 * TPR){ sum = hadd(sum, sv[j]); sum2 = hadd(sum2, sv[j + TPR]); }
                     if (j < end) sum = hadd(sum, sv[j]);
