@@ -232,6 +232,7 @@ extern "C" {
 int hb_spmm(hb_ctx *ctx, const hb_csr *A, char transa, char transb, int b_rows, int b_cols, const void *alpha, const void *B, int ldb,
             const void *beta, void *C, int ldc){
     HB_ARG(ctx && A && alpha && beta, "null");
+    hb_activate(ctx);
     HB_ARG(b_rows >= 0 && b_cols >= 0, "negative size");
     const bool an = hb_is_n(transa), bn = hb_is_n(transb);
     const int M = an ? A->rows : A->cols, K = an ? A->cols : A->rows, N = bn ? b_cols : b_rows;

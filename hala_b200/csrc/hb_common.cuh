@@ -104,6 +104,12 @@ int  hb_cuda_fail(cudaError_t e, const char *what);
 #define HB_ARG(cond, msg) do { if (!(cond)) { hb_set_error(std::string("invalid argument: ") + msg); return HB_ERR_ARG; } } while (0)
 #define HB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaPeekAtLastError(); if (e__ != cudaSuccess) return hb_cuda_fail(e__, "kernel launch"); } while (0)
 
+// makes the context's device the current one (the reference binds its vendor handles to the device of the engine and sets the device
+// in gpu_allocate, gpu/hala_cuda_common.hpp:255: engines for several devices may live in one process and are used in turn)
+static inline void hb_activate(const hb_ctx *ctx){
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) cudaSetDevice(ctx->device);
+}
 static inline size_t hb_dtype_size(int dtype){ return dtype == HB_F32 ? 4 : dtype == HB_F64 ? 8 : dtype == HB_C32 ? 8 : 16; }
 static inline bool   hb_is_n(char t){ return t == 'N' || t == 'n'; }
 static inline bool   hb_is_c(char t){ return t == 'C' || t == 'c'; }

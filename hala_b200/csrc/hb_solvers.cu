@@ -254,6 +254,7 @@ extern "C" {
 
 int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
     HB_ARG(ctx && A && b && x, "null");
+    hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "CG needs a square matrix");
     const int n = A->rows, dtype = A->dtype;
     const size_t es = hb_dtype_size(dtype);
@@ -316,6 +317,7 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
 int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, hb_precon_fn precon_fn, void *user, int *iters, double *res){
     if (!precon_fn) return hb_cg(ctx, A, b, x, tol, max_iter, iters, res);
     HB_ARG(ctx && A && b && x, "null");
+    hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "CG needs a square matrix");
     const int n = A->rows, dtype = A->dtype;
     const size_t es = hb_dtype_size(dtype);
@@ -375,6 +377,7 @@ int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int
 int hb_pgmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, hb_precon_fn precon_fn, void *user,
               int *iters, double *res){
     HB_ARG(ctx && A && b && x, "null");
+    hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
     HB_ARG(restart >= 1, "restart must be positive");
     if (A->rows == 0){ if (iters) *iters = 0; if (res) *res = 0; return HB_OK; }
@@ -385,6 +388,7 @@ int hb_pgmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, 
 
 int hb_gmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, int *iters, double *res){
     HB_ARG(ctx && A && b && x, "null");
+    hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
     HB_ARG(restart >= 1, "restart must be positive");
     if (A->rows == 0){ if (iters) *iters = 0; if (res) *res = 0; return HB_OK; }

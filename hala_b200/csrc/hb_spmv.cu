@@ -717,6 +717,7 @@ extern "C" {
 
 int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int *pntr, const int *indx, const void *vals, hb_csr **out){
     HB_ARG(ctx && out, "null");
+    hb_activate(ctx);
     HB_ARG(dtype >= HB_F32 && dtype <= HB_C64, "dtype");
     HB_ARG(rows >= 0 && cols >= 0 && nnz >= 0, "negative dimension");
     HB_ARG(rows == 0 || pntr, "pntr is null");
@@ -814,6 +815,7 @@ int hb_spmv_buffer_size(const hb_csr *A, char trans, size_t *bytes){ (void) tran
 
 int hb_spmv(hb_ctx *ctx, const hb_csr *A, char trans, const void *alpha, const void *x, const void *beta, void *y){
     HB_ARG(ctx && A && alpha && beta, "null");
+    hb_activate(ctx);
     const int ny = hb_is_n(trans) ? A->rows : A->cols;
     if (ny == 0) return HB_OK;
     HB_ARG(y, "y is null");
@@ -842,6 +844,7 @@ int hb_spmv(hb_ctx *ctx, const hb_csr *A, char trans, const void *alpha, const v
 
 int hb_spmv_dot(hb_ctx *ctx, const hb_csr *A, const void *x, void *y, void *dot_dev){
     HB_ARG(ctx && A && dot_dev, "null");
+    hb_activate(ctx);
     HB_ARG(A->cols >= A->rows, "hb_spmv_dot needs cols >= rows (x[i] pairs with y[i]; extra columns are ghost entries)");
     if (A->rows == 0){ HB_CUDA(cudaMemsetAsync(dot_dev, 0, hb_dtype_size(A->dtype), ctx->stream)); return HB_OK; }
     return hb_spmv_dot_internal(ctx, A, x, y, dot_dev, nullptr);

@@ -503,3 +503,39 @@ def test_blas1_negative_and_zero_increments(engine):
     gy.load(y)
     assert lib.hb_scal(engine.ctx, 1, n, ap, gy.ptr, -1) == 0
     np.testing.assert_array_equal(gy.unload(), y)
+
+
+def test_engines_on_two_devices_in_one_process():
+    """The reference's test mains create a gpu_engine for every device of the box in one process (tests/sparse_tests.cpp:52,
+    solvers_tests.cpp:59).  Kernel attributes (the opt-in to > 48 KB of dynamic shared memory, carve-out, occupancy) are per device: the
+    streaming SpMV, the multi right-hand-side product, the Gram-Schmidt kernels and a CG solve must work on device 1 after device 0 used them."""
+    if hb.gpu_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p, i, v = mg.lap3d27(16)
+    N = p.size - 1
+    x = mg.probe_x(N)
+    pc, ic, vc = mg.convdiff7(12)
+    results = []
+    for dev in (0, 1, 0):
+        e = hb.gpu_engine(dev)
+        gp, gi, gv = load_csr(e, p, i, v)
+        A = hb.make_sparse_matrix(e, N, gp, gi, gv)
+        gy = e.new_vector(np.float64)
+        A.gemv("N", 1.0, e.load(x), 0.0, gy)
+        y = gy.unload()
+        B = mg.probe_x(4 * N, seed=3)                       # SpMM, 4 columns (interleaved streaming kernel)
+        gB, gC = e.load(B), e.new_vector(np.float64, 4 * N)
+        A.gemm("N", "N", N, 4, 1.0, gB, N, 0.0, gC, N)
+        Cm = gC.unload()
+        gx = e.new_vector(np.float64)
+        it, res = hb.solve_cg(e, 1e-8, 10 ** 6, gp, gi, gv, e.load(mg.rhs(N)), gx, matrix=A)
+        gxg = e.new_vector(np.float64)                      # GMRES: TMA-staged Gram-Schmidt kernels
+        itg, _ = hb.solve_gmres(e, 1e-8, 10 ** 6, 20, *load_csr(e, pc, ic, vc), e.load(mg.rhs(12 ** 3)), gxg)
+        results.append((y, Cm, it, gx.unload(), itg, gxg.unload()))
+        del A, gy, gB, gC, gx, gxg, gp, gi, gv
+    for r in results[1:]:
+        np.testing.assert_array_equal(r[0], results[0][0])
+        np.testing.assert_array_equal(r[1], results[0][1])
+        assert r[2] == results[0][2] and r[4] == results[0][4]
+        np.testing.assert_array_equal(r[3], results[0][3])
+        np.testing.assert_array_equal(r[5], results[0][5])
