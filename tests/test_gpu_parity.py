@@ -539,3 +539,34 @@ def test_engines_on_two_devices_in_one_process():
         assert r[2] == results[0][2] and r[4] == results[0][4]
         np.testing.assert_array_equal(r[3], results[0][3])
         np.testing.assert_array_equal(r[5], results[0][5])
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "c32", "c64"])
+def test_heavy_tailed_rows_plain_and_fused_dot(engine, dt):
+    """Power-law row lengths take the virtual-row form of the streaming kernel (segments + tile table + combine kernel): the plain
+    product with alpha / beta and the product fused with <x, y> (what hb_cg launches) against left-to-right numpy sums, every row."""
+    import ctypes as C
+    from hala_b200.capi import lib
+    N = 6000
+    p, i, v = mg.powerlaw(N=N, lmax=1500, dtype=dt)
+    assert np.diff(p).max() > 16 * (i.size / N + 1)                   # heavy-tailed by hb_csr_create's own test
+    x = mg.probe_x(N, dt, seed=17)
+    gp, gi, gv = load_csr(engine, p, i, v)
+    A = hb.make_sparse_matrix(engine, N, gp, gi, gv)
+    wide = np.complex128 if dt.startswith("c") else np.float64
+    rows = np.repeat(np.arange(N), np.diff(p))
+    ref = np.zeros(N, dtype=wide)
+    np.add.at(ref, rows, v.astype(wide) * x[i].astype(wide))
+    scale = np.zeros(N)
+    np.add.at(scale, rows, np.abs(v) * np.abs(x[i]))
+    tol = SPMV_TOL[dt]
+    gx, gy = engine.load(x), engine.load(x.copy())
+    A.gemv("N", 2.0, gx, -0.5, gy)
+    assert np.max(np.abs(gy.unload() - (2.0 * ref - 0.5 * x)) / (2 * scale + np.abs(x))) <= tol
+    gd = engine.new_vector(NP[dt], 4)
+    assert lib.hb_spmv_dot(engine.ctx, A.h, gx.ptr, gy.ptr, gd.ptr) == 0
+    y = gy.unload()
+    assert np.max(np.abs(y - ref) / scale) <= tol
+    d = gd.unload()[0]
+    want = np.vdot(x.astype(wide), ref)                               # conj(x) . (A x)
+    assert abs(d - want) <= 50 * tol * np.sum(np.abs(x) * scale)
