@@ -7,6 +7,15 @@
 #include <string>
 #include "../../include/halab200.h"
 
+// NVTX ranges around the library's phases (header-only nvtx3: a no-op unless a profiler injected itself; SURVEY.md §5 tracing)
+#include <nvtx3/nvToolsExt.h>
+struct hb_range {
+    explicit hb_range(const char *name){ nvtxRangePushA(name); }
+    ~hb_range(){ nvtxRangePop(); }
+    hb_range(const hb_range&) = delete;
+    hb_range& operator=(const hb_range&) = delete;
+};
+
 // ----------------------------------------------------------------------------------------------------------------
 // context / matrix objects behind the opaque C handles
 // ----------------------------------------------------------------------------------------------------------------

@@ -351,6 +351,7 @@ void peer_release(hb_dist *d){
 // Collective over all ranks.  HB_OK: the peer path is ready for element size `es`; HB_ERR_UNSUPPORTED: agreed by ALL ranks
 // that it is not available (the callers then take the NCCL path); anything else is an error.
 int peer_setup(hb_dist *d, size_t es){
+    hb_range nvtx_range("hb_dist: peer transport set-up");
     if (d->peer_state == 1 && d->peer_es == es) return HB_OK;
     if (d->peer_state == -1) return HB_ERR_UNSUPPORTED;
     hb_ctx *ctx = d->ctx;
@@ -800,6 +801,7 @@ int hb_dist_spmv(hb_dist *d, const hb_csr *A, void *x_ext, void *y){
 }
 
 int hb_dist_cg(hb_dist *d, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+    hb_range nvtx_range("hb_dist_cg");
     HB_ARG(d && A && b && x, "null");
     HB_ARG(A->rows == d->n_owned && A->cols == d->n_owned + d->n_ghost, "matrix shape does not match the exchange plan");
     hb_ctx *ctx = d->ctx;

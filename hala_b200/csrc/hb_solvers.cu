@@ -253,6 +253,7 @@ int gmres_typed(hb_ctx *ctx, hb_dist *dist, const hb_csr *A, const T *b, T *x, d
 extern "C" {
 
 int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, int *iters, double *res){
+    hb_range nvtx_range("hb_cg");
     HB_ARG(ctx && A && b && x, "null");
     hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "CG needs a square matrix");
@@ -316,6 +317,7 @@ int hb_cg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int 
 // by the done flag (the caller's preconditioner still runs for them, on a residual that no longer changes).
 int hb_pcg(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_iter, hb_precon_fn precon_fn, void *user, int *iters, double *res){
     if (!precon_fn) return hb_cg(ctx, A, b, x, tol, max_iter, iters, res);
+    hb_range nvtx_range("hb_pcg");
     HB_ARG(ctx && A && b && x, "null");
     hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "CG needs a square matrix");
@@ -387,6 +389,7 @@ int hb_pgmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, 
 }
 
 int hb_gmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, int *iters, double *res){
+    hb_range nvtx_range("hb_gmres");
     HB_ARG(ctx && A && b && x, "null");
     hb_activate(ctx);
     HB_ARG(A->rows == A->cols, "GMRES needs a square matrix");
@@ -397,6 +400,7 @@ int hb_gmres(hb_ctx *ctx, const hb_csr *A, const void *b, void *x, double tol, i
 }
 
 int hb_dist_gmres(hb_dist *dist, const hb_csr *A, const void *b, void *x, double tol, int max_outer, int restart, int cproj, int *iters, double *res){
+    hb_range nvtx_range("hb_dist_gmres");
     HB_ARG(dist && A && b && x, "null");
     HB_ARG(restart >= 1, "restart must be positive");
     hb_ctx *ctx = hb_dist_context(dist);

@@ -514,6 +514,7 @@ static int launch_pipe_vs(hb_ctx *ctx, const hb_csr *A, const T *x, T *y, scalar
 // 2^22-row power-law matrix): segments of at most SEG = (CAP - 8) / 4 entries, so that ANY four consecutive virtual rows fit a ring stage
 // and tiles can start at multiples of four virtual rows (16-byte aligned slices of vpntr for the bulk copies).
 static int vsplit_build(hb_ctx *ctx, hb_csr *A){
+    hb_range nvtx_range("hb_csr_create: virtual-row tables");
     const size_t es = hb_dtype_size(A->dtype);
     const int cap = VS_THREADS * (es == 16 ? 4 : 8) / VS_SLOT_DIV;
     // lanes per row of the summation phase only (the gathers are dealt by non-zero): half of what the general kernel would take, so
@@ -716,6 +717,7 @@ int hb_csr_halo_order(hb_ctx *ctx, const hb_csr *A, int *trot, int *twait){
 extern "C" {
 
 int hb_csr_create(hb_ctx *ctx, int dtype, int rows, int cols, int nnz, const int *pntr, const int *indx, const void *vals, hb_csr **out){
+    hb_range nvtx_range("hb_csr_create (analysis)");
     HB_ARG(ctx && out, "null");
     hb_activate(ctx);
     HB_ARG(dtype >= HB_F32 && dtype <= HB_C64, "dtype");
