@@ -1,5 +1,6 @@
+"""27-point 128^3 SpMV: 128- vs 256-thread CTAs of the streaming kernel (HB_PIPE_CFG) x resident CTAs the carve-out is sized for (HB_PIPE_CTAS)."""
 import json, os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import hala_b200 as hb
 from hala_b200 import devgen, matgen as mg
