@@ -16,10 +16,12 @@
 // where the reference's own templates call solve_cg / solve_gmres unqualified; stop_criteria is only declared here.
 #include "hala_gpu_ilu.hpp"
 #include <exception>
+#include <functional>
 
 namespace hala{
 
 template<typename precision> struct stop_criteria;          // defined in hex/solvers/hala_solvers_core.hpp:52-71
+template<class cengine, class vec> struct engined_vector;   // defined in wax/hala_noengine_structs.hpp:153-216
 
 //! extension: says "no preconditioner" in a way the gpu_engine solvers can see (a lambda that copies cannot be told from a real
 //! preconditioner and costs the iteration a copy and a dot product).  Usable with every engine: it copies x to r.
@@ -75,6 +77,28 @@ int prepare(gpu_engine const &engine, VectorLikeP const &pntr, VectorLikeI const
     return num_rows;
 }
 
+//! Takes a preconditioner written for engine-bound vectors (preconditioner_noe, hala_solvers_core.hpp:139-142) to the gpu_vector
+//! form of the fused solvers: the solver's arrays are moved, as views, into the owning engined_vector<gpu_engine, gpu_vector<T>>
+//! objects the reference would hand over (decltype(new_vector(vals)), hala_solvers_cg.hpp:198).
+template<typename T, class Precon> struct unbound_precon{
+    Precon &precon;
+    gpu_engine const &engine;
+    void operator()(gpu_vector<T> const &in, gpu_vector<T> &out) const{
+        engined_vector<gpu_engine, gpu_vector<T>> bin(engine), bout(engine);
+        bin.vector() = gpu_vector<T>::view(engine.device(), const_cast<T*>(in.data()), in.size());
+        bout.vector() = gpu_vector<T>::view(engine.device(), out.data(), out.size());
+        precon(const_cast<engined_vector<gpu_engine, gpu_vector<T>> const&>(bin), bout);
+        if (bout.vector().data() != out.data()) out = std::move(bout.vector());     // storage of its own: the bridge copies it back
+    }
+};
+//! A preconditioner already typed as the reference's std::function (preconditioner_noe) matches the reference's no-engine solve_cg
+//! exactly; partial ordering cannot rank the two templates then (gcc: ambiguous), so the overload below steps aside for it.
+template<class F> struct is_std_function : std::false_type{};
+template<class S> struct is_std_function<std::function<S>> : std::true_type{};
+
+template<typename T, class Precon> unbound_precon<T, Precon> unbind(gpu_engine const &engine, Precon &precon){ return {precon, engine}; }
+template<typename T> identity_preconditioner unbind(gpu_engine const&, identity_preconditioner&){ return {}; }
+
 }
 
 //! hala::solve_cg on gpu_engine: hb_pcg (identity_preconditioner: hb_cg).  Returns the number of operator applications.
@@ -96,6 +120,23 @@ int solve_cg(gpu_engine const &engine, stop_criteria<get_precision_type<VectorLi
     if (bridge.error) std::rethrow_exception(bridge.error);
     check_hb(status, "hala::solve_cg(gpu_engine)");
     return iterations;
+}
+
+//! hala::solve_cg(stop, ...) without an engine argument, on vectors bound to a gpu_engine (bind_engine_vector): the reference runs
+//! solve_cg_core on them (hala_solvers_cg.hpp:181-226); here they are unbound and take the fused iteration above.  The no-engine
+//! solve_cg_ilu (:295-305) calls hala::solve_cg(stop, ...) and lands here too; the no-engine solve_gmres already forwards to the
+//! engine form (hala_solvers_gmres.hpp:305-320), i.e. to the overload below.  A preconditioner passed as a std::function object
+//! (not a lambda or functor) keeps the reference's loop: see b200_solvers::is_std_function.
+template<class VectorLikeP, class VectorLikeI, class VectorLikeV, class VectorLikeX, class VectorLikeB, class Precon>
+std::enable_if_t<!b200_solvers::is_std_function<Precon>::value, int>
+solve_cg(stop_criteria<get_precision_type<engined_vector<gpu_engine, VectorLikeV>>> const &stop,
+             engined_vector<gpu_engine, VectorLikeP> const &pntr, engined_vector<gpu_engine, VectorLikeI> const &indx,
+             engined_vector<gpu_engine, VectorLikeV> const &vals, Precon precon,
+             engined_vector<gpu_engine, VectorLikeB> const &b, engined_vector<gpu_engine, VectorLikeX> &x){
+    assert( check_engines(pntr, indx, vals, b, x) );
+    using T = typename engined_vector<gpu_engine, VectorLikeX>::value_type;
+    gpu_engine const &engine = x.engine();
+    return solve_cg(engine, stop, pntr.vector(), indx.vector(), vals.vector(), b200_solvers::unbind<T>(engine, precon), b.vector(), x.vector());
 }
 
 //! hala::solve_cg_ilu on gpu_engine with a ready factorisation: the ILU application runs between the fused kernels.

@@ -184,6 +184,41 @@ template<typename T> void fused_front_doors(){
     gy3.unload(yig);
     hassert(std::abs(gic - gig) <= 2);
     hassert(testvec(yig, yic, 1.E+6 * hala::norm2(yic)));
+
+    // 7. the no-engine forms on vectors bound to the engine (bind_engine_vector): same fused iteration, same launch counts; the
+    //    preconditioner sees engined vectors; one typed as the reference's std::function (preconditioner_noe) must still compile and solve
+    indx.clear(); vals.clear();
+    lap2d<T>(n, pntr, indx, vals);
+    gv.load(vals);
+    hala::gpu_vector<T> gx7(egpu.device()), gx8(egpu.device()), gx9(egpu.device()), gx10(egpu.device());
+    auto bp = hala::bind_engine_vector(egpu, gp); auto bi = hala::bind_engine_vector(egpu, gi); auto bv = hala::bind_engine_vector(egpu, gv);
+    auto bb = hala::bind_engine_vector(egpu, gb);
+    auto bx7 = hala::bind_engine_vector(egpu, gx7); auto bx8 = hala::bind_engine_vector(egpu, gx8);
+    auto bx9 = hala::bind_engine_vector(egpu, gx9); auto bx10 = hala::bind_engine_vector(egpu, gx10);
+    std::vector<T> x7, x8, x9, x10;
+    l0 = launches();
+    int it7 = hala::solve_cg(stop, bp, bi, bv, [&](auto const &in, auto &out)->void{ hala::vcopy(in, out); }, bb, bx7);
+    per_it = (launches() - l0) / it7;
+    gx7.unload(x7);
+    hassert(it7 == it1);
+    hassert(per_it <= 5);
+    hassert(testvec(x7, xcpu, 1.E+6 * hala::norm2(xcpu)));
+    l0 = launches();
+    int it8 = hala::solve_cg(stop, bp, bi, bv, hala::identity_preconditioner(), bb, bx8);
+    per_it = (launches() - l0) / it8;
+    gx8.unload(x8);
+    hassert(it8 == it2);
+    hassert(per_it <= 3);
+    hassert(testvec(x8, xcpu, 1.E+6 * hala::norm2(xcpu)));
+    hala::preconditioner_noe<decltype(bv)> typed = [&](auto const &in, auto &out)->void{ hala::vcopy(in, out); hala::scal(2.0, out); };
+    int it9 = hala::solve_cg(stop, bp, bi, bv, typed, bb, bx9);       // a scaled identity, as a std::function: the reference's loop
+    gx9.unload(x9);
+    hassert(std::abs(it9 - it_cpu) <= 2);
+    hassert(testvec(x9, xcpu, 1.E+6 * hala::norm2(xcpu)));
+    int it10 = hala::solve_cg_ilu(stop, bp, bi, bv, ilu, bb, bx10);    // the reference's template: calls hala::solve_cg(stop, ...)
+    gx10.unload(x10);
+    hassert(it10 == ig);
+    hassert(testvec(x10, xic, 1.E+6 * hala::norm2(xic)));
 }
 
 // Row f3, staging half: page-locked containers through load / unload / gpu_bind_vector and a mixed_engine solve.
