@@ -56,26 +56,37 @@ static void run(const char *name, int dims, int n, int K, bool with_reference_lo
     auto raw = [&](){ zero(); hala::check_hb(hb_cg(engine, matrix.csr(), gb.data(), gx.data(), 0.0, K + 1, &it, &res), "hb_cg"); };
     auto tag = [&](){ zero(); it = hala::solve_cg(engine, stop, gp, gi, gv, hala::identity_preconditioner(), gb, gx); };
     auto cpy = [&](){ zero(); it = hala::solve_cg(engine, stop, gp, gi, gv, [&](auto const &in, auto &out)->void{ hala::vcopy(engine, in, out); }, gb, gx); };
-    // the reference's own loop (solve_cg_core through BLAS-1 calls on this backend): what the template call ran before the overloads
-    auto ref = [&](){
+    // the no-engine form on engine-bound vectors with a copy lambda: unbound by hala_gpu_solvers.hpp, the fused iteration again
+    auto noe = [&](){
         zero();
         auto p = hala::bind_engine_vector(engine, gp); auto i = hala::bind_engine_vector(engine, gi); auto v = hala::bind_engine_vector(engine, gv);
         auto bb = hala::bind_engine_vector(engine, gb); auto xx = hala::bind_engine_vector(engine, gx);
         it = hala::solve_cg(stop, p, i, v, [&](auto const &in, auto &out)->void{ hala::vcopy(in, out); }, bb, xx);
     };
-    raw(); tag(); cpy();
+    // the reference's own loop (solve_cg_core through BLAS-1 calls on this backend): what the template call ran before the overloads.
+    // A preconditioner typed as the reference's std::function is the one call the overloads leave to it.
+    auto ref = [&](){
+        zero();
+        auto p = hala::bind_engine_vector(engine, gp); auto i = hala::bind_engine_vector(engine, gi); auto v = hala::bind_engine_vector(engine, gv);
+        auto bb = hala::bind_engine_vector(engine, gb); auto xx = hala::bind_engine_vector(engine, gx);
+        hala::preconditioner_noe<decltype(v)> typed = [&](auto const &in, auto &out)->void{ hala::vcopy(in, out); };
+        it = hala::solve_cg(stop, p, i, v, typed, bb, xx);
+    };
+    raw(); tag(); cpy(); noe();
     long long l0 = launches();
     const double t_raw = seconds(engine, raw); const long long l_raw = launches() - l0; l0 = launches();
     const double t_tag = seconds(engine, tag); const long long l_tag = launches() - l0; l0 = launches();
     const double t_cpy = seconds(engine, cpy); const long long l_cpy = launches() - l0; l0 = launches();
+    const double t_noe = seconds(engine, noe); const long long l_noe = launches() - l0; l0 = launches();
     double t_ref = 0; long long l_ref = 0;
     if (with_reference_loop){ ref(); l0 = launches(); t_ref = seconds(engine, ref); l_ref = launches() - l0; }
     std::printf("{\"workload\": \"%s\", \"rows\": %zu, \"nnz\": %zu, \"iterations\": %d, "
-                "\"hb_cg_its\": %.2f, \"template_identity_tag_its\": %.2f, \"template_copy_lambda_its\": %.2f, \"reference_loop_on_our_blas1_its\": %.2f, "
-                "\"launches_per_it\": {\"hb_cg\": %.2f, \"identity_tag\": %.2f, \"copy_lambda\": %.2f, \"reference_loop\": %.2f}, "
+                "\"hb_cg_its\": %.2f, \"template_identity_tag_its\": %.2f, \"template_copy_lambda_its\": %.2f, \"template_noengine_copy_lambda_its\": %.2f, "
+                "\"reference_loop_on_our_blas1_its\": %.2f, "
+                "\"launches_per_it\": {\"hb_cg\": %.2f, \"identity_tag\": %.2f, \"copy_lambda\": %.2f, \"noengine_copy_lambda\": %.2f, \"reference_loop\": %.2f}, "
                 "\"tag_vs_hb_cg\": %.3f, \"copy_lambda_vs_hb_cg\": %.3f}\n",
-                name, N, nnz, K, K / t_raw, K / t_tag, K / t_cpy, with_reference_loop ? K / t_ref : 0.0,
-                (double) l_raw / K, (double) l_tag / K, (double) l_cpy / K, (double) l_ref / K, t_raw / t_tag, t_raw / t_cpy);
+                name, N, nnz, K, K / t_raw, K / t_tag, K / t_cpy, K / t_noe, with_reference_loop ? K / t_ref : 0.0,
+                (double) l_raw / K, (double) l_tag / K, (double) l_cpy / K, (double) l_noe / K, (double) l_ref / K, t_raw / t_tag, t_raw / t_cpy);
     std::fflush(stdout);
 }
 
